@@ -1,0 +1,123 @@
+/* include/tcb200.h -- C ABI of libtcb200.so: the B200 (sm_100a) implementation of tileconv's
+ * TIS/MOS -> TBC/MBC encode hot path (palette expand + BC1/BC2/BC3 block fitting).
+ *
+ * Plain C: pointers and sizes only, no C++ or torch types.  Return convention follows the
+ * reference's (everything there is noexcept and reports 0 / nullptr / false):
+ * functions returning int give 0 on success and a negative TCB200_E_* code on failure, never throw;
+ * the message is available from tcb200_last_error().  There is NO CPU fallback: without a usable
+ * CUDA device every compute entry point fails with TCB200_E_NODEVICE.
+ *
+ * The reference has no FFI of its own (single C++ binary); each entry point below names the
+ * reference interface it stands in for, so that a maintainer can bind it from the reference's
+ * Converter / TileThreadPool seams.
+ *
+ * Data layouts (all little-endian, identical to the reference's in-memory tiles):
+ *   input tile record  = 5120 bytes: 1024 B palette (256 x {B,G,R,x}) then 4096 B index area.
+ *                        A w x h tile (w,h <= 64) keeps its indices in the first w*h bytes with
+ *                        row pitch w  (tileconv/graphics.cpp:101-119 TIS, :322-342 MOS).
+ *   output tile record = `stride` bytes, stride = tcb200_record_size(type,64,64): u16 w, u16 h,
+ *                        then ceil(w/4)*ceil(h/4) blocks in row-major block order, 8 B (BC1) or
+ *                        16 B (BC2/BC3) each  (tileconv/converter_dxt.cpp:109-144, FORMATS:36-41).
+ *                        Only the first tcb200_record_size(type,w,h) bytes of a record are defined.
+ */
+#ifndef TCB200_H
+#define TCB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TCB200_TILE_RECORD 5120
+
+#define TCB200_OK            0
+#define TCB200_E_ARG       (-1)   /* bad argument (null pointer, type/quality/size out of range) */
+#define TCB200_E_NODEVICE  (-2)   /* no CUDA device / device index out of range */
+#define TCB200_E_CUDA      (-3)   /* a CUDA call failed; see tcb200_last_error() */
+#define TCB200_E_NOMEM     (-4)   /* allocation failed */
+
+typedef struct tcb200_ctx tcb200_ctx;
+
+/* Number of usable CUDA devices (0 when there is none).  Stands in for getThreadPoolAutoThreads()
+ * (tileconv/tilethreadpool_base.h:38): "how wide can the fan-out be". */
+int tcb200_device_count(void);
+
+/* getRequiredSpace(w,h) + HEADER_TILE_ENCODED_SIZE for pixel type 1,2,3; 0 on error
+ * (tileconv/converter_dxt.cpp:41-62, tileconv/tiledata.cpp:123). */
+int tcb200_record_size(int type, int width, int height);
+
+/* One encoder context = one device, one pixel type (-t 1/2/3 = BC1/BC2/BC3,
+ * tileconv/options.cpp:95-110) and one encode quality (-q second digit 0..9, mapped onto
+ * RangeFit / ClusterFit / weighted / iterative exactly as ConverterDxt::getFlags does,
+ * tileconv/converter_dxt.cpp:179-212).  max_batch_tiles sizes the device-side double buffers
+ * used by tcb200_encode (0 = default).  Replaces "new ConverterDxt per tile"
+ * (tileconv/tiledata.cpp:114-121) + createThreadPool (tileconv/tilethreadpool_base.h:44).
+ * Returns NULL on failure (message via tcb200_last_error(NULL)). */
+tcb200_ctx* tcb200_create(int device, int type, int quality, int max_batch_tiles);
+void        tcb200_destroy(tcb200_ctx* ctx);
+
+/* Last error message of this context (or of the failed tcb200_create when ctx == NULL). */
+const char* tcb200_last_error(const tcb200_ctx* ctx);
+
+int tcb200_type(const tcb200_ctx* ctx);
+int tcb200_quality(const tcb200_ctx* ctx);
+int tcb200_device(const tcb200_ctx* ctx);
+int tcb200_record_stride(const tcb200_ctx* ctx);   /* = tcb200_record_size(type, 64, 64) */
+
+/* Host-to-host batch encode: n tile records in `tiles` (host memory, ideally pinned), optional
+ * per-tile sizes `wh` (n x {u16 w, u16 h}; NULL = all 64x64), n output records written to `out`
+ * (host).  Internally the batch is cut into chunks that are uploaded, encoded and downloaded on
+ * separate CUDA streams with double buffering; returns when `out` is complete.
+ * This is the batched form of Converter::convert(palette, indexed, encoded, w, h)
+ * (tileconv/converter.h:85) as driven by TileData::encode (tileconv/tiledata.cpp:111-162, -u path). */
+int tcb200_encode(tcb200_ctx* ctx, const uint8_t* tiles, const uint16_t* wh, int n, uint8_t* out);
+
+/* Device-resident variant: all three pointers are device pointers on ctx's device; the kernel is
+ * enqueued on `stream` (a cudaStream_t passed as void*, NULL = the context's compute stream) and
+ * the call returns without synchronising. */
+int tcb200_encode_device(tcb200_ctx* ctx, const void* d_tiles, const void* d_wh, int n, void* d_out, void* stream);
+
+/* Asynchronous slab interface used by the batch queue (host side of TileThreadPool's role,
+ * tileconv/tilethreadpool_base.h:64-81): the context owns `slabs` pinned input/output slabs of
+ * max_batch_tiles records.  Fill tcb200_slab_input(), submit, later wait and read
+ * tcb200_slab_output().  Slabs progress independently (upload, kernel and download of different
+ * slabs overlap). */
+int      tcb200_slab_count(const tcb200_ctx* ctx);
+int      tcb200_slab_capacity(const tcb200_ctx* ctx);
+uint8_t* tcb200_slab_input(tcb200_ctx* ctx, int slab);     /* capacity x 5120 B, pinned */
+uint16_t* tcb200_slab_sizes(tcb200_ctx* ctx, int slab);    /* capacity x {w,h}, pinned  */
+uint8_t* tcb200_slab_output(tcb200_ctx* ctx, int slab);    /* capacity x stride B, pinned */
+int      tcb200_slab_submit(tcb200_ctx* ctx, int slab, int n);
+int      tcb200_slab_wait(tcb200_ctx* ctx, int slab);      /* blocks until that slab's output is ready */
+int      tcb200_slab_ready(tcb200_ctx* ctx, int slab);     /* 1 ready, 0 in flight, <0 error */
+
+/* Pinned host memory for callers that want zero-copy-staging uploads (TileData's buffers are
+ * plain new[] in the reference, tileconv/graphics.cpp:101-103). */
+void* tcb200_host_alloc(size_t bytes);
+void  tcb200_host_free(void* p);
+
+/* Colors::palToARGB (tileconv/colors.cpp:42-59) for n 64x64 tile records: writes n x 4096 pixels
+ * of 4 bytes in memory order B,G,R,A to host memory `bgra`.  Exposed for parity tests of the
+ * expand stage; the encode kernels expand in shared memory and never write pixels to HBM. */
+int tcb200_pal_to_argb(tcb200_ctx* ctx, const uint8_t* tiles, int n, uint8_t* bgra);
+
+/* Kernel-only timing aid for bench.py: runs the encode kernel `reps` times on device-resident data
+ * on the context's compute stream and returns the mean milliseconds per launch measured with CUDA
+ * events on that stream (negative error code on failure). */
+float tcb200_time_kernel_ms(tcb200_ctx* ctx, const void* d_tiles, const void* d_wh, int n, void* d_out, int reps);
+
+/* Measured FP32 pipe peak of the device, for the ALU roofline: a register-resident loop of
+ * independent fused multiply-adds (fused != 0) or of separate multiply and add instructions
+ * (fused == 0, the form the bit-exact fitters are restricted to).  Returns lane-operations per
+ * second counting one per FMUL/FADD/FFMA instruction lane (so FLOP/s = 2x for fused). */
+double tcb200_fp32_peak(tcb200_ctx* ctx, int fused);
+
+/* Kernels launched by this context so far (bench.py's gpu_launches). */
+long long tcb200_launch_count(const tcb200_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TCB200_H */

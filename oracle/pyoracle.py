@@ -1,0 +1,168 @@
+"""oracle/pyoracle.py -- TEST INFRASTRUCTURE.  ctypes binding of the CPU oracle (oracle/libtco.so =
+squish_oracle.cpp + tile_oracle.cpp) and, when present, of the reference-glue build
+(oracle/_ref/libtileconv_ref.so).  Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs may import this module."""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_TCO: Optional[ctypes.CDLL] = None
+_REF: Optional[ctypes.CDLL] = None
+
+
+class Counters(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_ulonglong) for n in
+                ("blocks", "single_blocks", "range_blocks", "cluster_blocks", "cand3", "cand4", "sweeps3", "sweeps4", "points")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+def build(ref: bool = True) -> None:
+    """Compiles the oracle (and, where /root/reference exists, the reference-glue build)."""
+    subprocess.run(["make", "-C", _HERE, "libtco.so"], check=True, capture_output=True)
+    if ref and os.path.isdir("/root/reference/tileconv"):
+        subprocess.run(["make", "-C", _HERE, "ref"], check=True, capture_output=True)
+
+
+def oracle() -> ctypes.CDLL:
+    global _TCO
+    if _TCO is None:
+        path = os.path.join(_HERE, "libtco.so")
+        if not os.path.exists(path):
+            build(ref=False)
+        _TCO = ctypes.CDLL(path)
+        _TCO.tco_encode_tile.restype = ctypes.c_int
+        _TCO.tco_required_space.restype = ctypes.c_int
+        _TCO.tco_decode_tile.restype = ctypes.c_int
+        _TCO.tco_pal_to_argb.restype = ctypes.c_int
+        _TCO.tco_squish_flags.restype = ctypes.c_int
+    return _TCO
+
+
+def reference() -> Optional[ctypes.CDLL]:
+    """The reference's own glue linked with the restated squish, or None if it was never built."""
+    global _REF
+    if _REF is None:
+        path = os.path.join(_HERE, "_ref", "libtileconv_ref.so")
+        if not os.path.exists(path):
+            return None
+        _REF = ctypes.CDLL(path)
+        _REF.tcref_encode_tile.restype = ctypes.c_int
+        _REF.tcref_encode_tiles.restype = ctypes.c_int
+        _REF.tcref_selftest.restype = ctypes.c_int
+        if _REF.tcref_selftest() != 1:
+            raise RuntimeError("oracle/_ref: Converter::ReorderColors mis-compiled (SURVEY.md F3, known answer KA1)")
+    return _REF
+
+
+def _p(a: np.ndarray):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def record_size(type_: int, w: int = 64, h: int = 64) -> int:
+    s = oracle().tco_required_space(type_, w, h)
+    return s + 4 if s else 0
+
+
+def encode_tile(palette: np.ndarray, indexed: np.ndarray, w: int, h: int, type_: int, quality: int) -> np.ndarray:
+    palette = np.ascontiguousarray(palette, np.uint8); indexed = np.ascontiguousarray(indexed, np.uint8)
+    out = np.zeros(4 + 4096, np.uint8)
+    n = oracle().tco_encode_tile(_p(palette), _p(indexed), w, h, type_, quality, _p(out))
+    return out[:n].copy()
+
+
+def encode_tiles(tiles: np.ndarray, type_: int, quality: int, threads: int = 1) -> np.ndarray:
+    tiles = np.ascontiguousarray(tiles, np.uint8).reshape(-1, 5120)
+    n = tiles.shape[0]
+    out = np.zeros((n, record_size(type_)), np.uint8)
+    oracle().tco_encode_tiles(_p(tiles), n, type_, quality, _p(out), threads)
+    return out
+
+
+def encode_tiles_wh(tiles: np.ndarray, wh: np.ndarray, type_: int, quality: int) -> np.ndarray:
+    """Per-tile sizes; output records padded to the 64x64 stride like libtcb200's."""
+    tiles = np.ascontiguousarray(tiles, np.uint8).reshape(-1, 5120)
+    n = tiles.shape[0]
+    out = np.zeros((n, record_size(type_)), np.uint8)
+    for i in range(n):
+        w, h = int(wh[i][0]), int(wh[i][1])
+        rec = encode_tile(tiles[i, :1024], tiles[i, 1024:1024 + w * h], w, h, type_, quality)
+        out[i, :len(rec)] = rec
+    return out
+
+
+def compress_block(rgba: np.ndarray, flags: int) -> np.ndarray:
+    rgba = np.ascontiguousarray(rgba, np.uint8).reshape(64)
+    out = np.zeros(16, np.uint8)
+    oracle().tco_compress_block(_p(rgba), flags, _p(out))
+    return out[:8] if (flags & 1) else out
+
+
+def squish_flags(type_: int, quality: int) -> int:
+    return int(oracle().tco_squish_flags(type_, quality))
+
+
+def gather_block(palette, indexed, w, h, bx, by) -> np.ndarray:
+    palette = np.ascontiguousarray(palette, np.uint8); indexed = np.ascontiguousarray(indexed, np.uint8)
+    out = np.zeros(64, np.uint8)
+    oracle().tco_gather_block(_p(palette), _p(indexed), w, h, bx, by, _p(out))
+    return out
+
+
+def pal_to_argb(indexed: np.ndarray, palette: np.ndarray) -> np.ndarray:
+    palette = np.ascontiguousarray(palette, np.uint8); indexed = np.ascontiguousarray(indexed, np.uint8)
+    out = np.zeros((indexed.size, 4), np.uint8)
+    oracle().tco_pal_to_argb(_p(indexed), _p(palette), _p(out), ctypes.c_uint32(indexed.size))
+    return out
+
+
+def decode_tile(record: np.ndarray, type_: int) -> np.ndarray:
+    record = np.ascontiguousarray(record, np.uint8)
+    w = int(record[0]) | (int(record[1]) << 8); h = int(record[2]) | (int(record[3]) << 8)
+    out = np.zeros((h, w, 4), np.uint8)
+    n = oracle().tco_decode_tile(_p(record), type_, _p(out))
+    assert n == w * h * 4
+    return out
+
+
+def totals_reset() -> None:
+    oracle().tco_totals_reset()
+
+
+def totals() -> dict:
+    c = Counters()
+    oracle().tco_totals_get(ctypes.byref(c))
+    return c.as_dict()
+
+
+def single_colour_table(bits: int, colours: int) -> np.ndarray:
+    out = np.zeros(256 * 6, np.uint8)
+    oracle().squish_oracle_single_colour_table(bits, colours, _p(out))
+    return out.reshape(256, 2, 3)
+
+
+def ref_encode_tile(palette, indexed, w, h, type_, quality) -> np.ndarray:
+    lib = reference()
+    palette = np.ascontiguousarray(palette, np.uint8); indexed = np.ascontiguousarray(indexed, np.uint8)
+    out = np.zeros(8192, np.uint8)
+    n = lib.tcref_encode_tile(_p(palette), _p(indexed), w, h, type_, quality, _p(out), 8192)
+    return out[:n].copy()
+
+
+def ref_encode_tiles(tiles: np.ndarray, type_: int, quality: int, threads: int) -> np.ndarray:
+    lib = reference()
+    tiles = np.ascontiguousarray(tiles, np.uint8).reshape(-1, 5120)
+    n = tiles.shape[0]
+    rec = record_size(type_)
+    out = np.zeros((n, rec), np.uint8)
+    failed = lib.tcref_encode_tiles(_p(tiles), n, type_, quality, _p(out), rec, threads)
+    if failed:
+        raise RuntimeError(f"reference failed on {failed} tiles")
+    return out

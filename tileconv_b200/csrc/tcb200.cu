@@ -1,0 +1,608 @@
+// tileconv_b200/csrc/tcb200.cu -- kernels + the C ABI of include/tcb200.h.
+//
+// Build (see __graft_entry__.build):
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
+// -fmad=false is part of the numerics contract (bc_device.cuh).
+#include "bc_device.cuh"
+#include "../../include/tcb200.h"
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+
+namespace tcb {
+
+// ================================================================================================
+// kernels
+// ================================================================================================
+enum Mode { kRange = 0, kCluster = 1, kIterative = 2 };
+
+template <int TYPE> struct BlockWords { static constexpr int value = (TYPE == 1) ? 2 : 4; };
+
+// One CTA = one tile.  See bc_device.cuh for the phase structure.
+template <int TYPE, bool WEIGHT_ALPHA, int MODE>
+__global__ void __launch_bounds__(kThreads, (MODE == kRange) ? 4 : 3)
+encode_tiles_kernel(const uint8_t* __restrict__ tiles, const uint16_t* __restrict__ wh, int ntiles,
+                    uint8_t* __restrict__ out, int outStride)
+{
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  TileShared& T = *reinterpret_cast<TileShared*>(smem_raw);
+  WarpJobs* allJobs = reinterpret_cast<WarpJobs*>(smem_raw + sizeof(TileShared));
+  WarpScratch* allScratch = reinterpret_cast<WarpScratch*>(smem_raw + sizeof(TileShared) + sizeof(WarpJobs) * kWarps);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  WarpJobs& jobs = allJobs[warp];
+  constexpr int kWords = BlockWords<TYPE>::value;
+
+  T.unit[tid] = (float)tid / 255.0f;
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    // ---- stage the tile record: 320 x 128-bit coalesced loads -----------------------------------
+    {
+      const uint4* src = reinterpret_cast<const uint4*>(tiles + (size_t)tile * kTileRecord);
+      uint4* dst = reinterpret_cast<uint4*>(T.palette);      // palette[256] and index[4096] are contiguous
+      dst[tid] = __ldg(src + tid);
+      if (tid < 320 - kThreads) dst[kThreads + tid] = __ldg(src + kThreads + tid);
+    }
+    int w = 64, h = 64;
+    if (wh != nullptr) { w = wh[2 * tile]; h = wh[2 * tile + 1]; }
+    __syncthreads();
+
+    const int bw = (w + 3) >> 2, bh = (h + 3) >> 2, nblocks = bw * bh;
+    const bool keyed = T.palette[0] == 0x0000ff00u;          // colors.cpp:47
+    if (tid == 0) T.out[0] = (uint32_t)w | ((uint32_t)h << 16);
+
+    // ---- phase A: thread <-> block --------------------------------------------------------------
+    uint8_t pending = 0xff;
+    if (tid < nblocks) {
+      const int bx = tid % bw, by = tid / bw;
+      uint32_t px[16];
+#pragma unroll
+      for (int p = 0; p < 16; ++p) px[p] = fetch_pixel(T, 4 * bx + (p & 3), 4 * by + (p >> 2), w, h, keyed);
+
+      uint32_t* dstBlock = T.out + 1 + kWords * tid;
+      if (TYPE == 2) { uint2 a = alpha_dxt3(px); dstBlock[0] = a.x; dstBlock[1] = a.y; }
+      if (TYPE == 3) { uint2 a = alpha_dxt5(px); dstBlock[0] = a.x; dstBlock[1] = a.y; }
+      uint32_t* dstColour = dstBlock + (TYPE == 1 ? 0 : 2);
+
+      const BlockSet s = build_colour_set<TYPE, WEIGHT_ALPHA>(px, jobs, lane);
+      if (s.count == 1) {
+        uint2 c = single_colour_block<TYPE>(T, jobs.key[0][lane], s, s.disabled != 0u);
+        dstColour[0] = c.x; dstColour[1] = c.y;
+      } else if (MODE == kRange || s.count == 0) {
+        float axis[3] = { 0.0f, 0.0f, 0.0f };
+        if (s.count > 0) principal_axis(T, jobs, lane, s.count, axis);
+        uint2 c = range_fit_block<TYPE>(T, jobs, lane, s, axis);
+        dstColour[0] = c.x; dstColour[1] = c.y;
+      } else {
+        float axis[3];
+        principal_axis(T, jobs, lane, s.count, axis);
+        jobs.axis[0][lane] = axis[0]; jobs.axis[1][lane] = axis[1]; jobs.axis[2][lane] = axis[2];
+        jobs.remapLo[lane] = s.remapLo; jobs.remapHi[lane] = s.remapHi;
+        jobs.disabled[lane] = (uint16_t)s.disabled;
+        pending = (uint8_t)s.count;
+      }
+    }
+    jobs.count[lane] = pending;
+    __syncwarp();
+
+    // ---- phase B: warp <-> block ----------------------------------------------------------------
+    if (MODE != kRange) {
+      WarpScratch& sc = allScratch[warp];
+      constexpr int iterations = (MODE == kIterative) ? kMaxIterations : 1;
+#pragma unroll 1
+      for (int slot = 0; slot < 32; ++slot) {
+        const int n = jobs.count[slot];
+        if (n == 0xff) continue;
+        float x = 0.0f, y = 0.0f, z = 0.0f, wgt = 0.0f;
+        if (lane < n) {
+          const uint32_t k = jobs.key[lane][slot];
+          x = T.unit[k & 255u]; y = T.unit[(k >> 8) & 255u]; z = T.unit[(k >> 16) & 255u];
+          wgt = jobs.weight[lane][slot];
+        }
+        const float principle[3] = { jobs.axis[0][slot], jobs.axis[1][slot], jobs.axis[2][slot] };
+        const uint32_t remapLo = jobs.remapLo[slot], remapHi = jobs.remapHi[slot], disabled = jobs.disabled[slot];
+        FitResult best;
+        best.err = FLT_MAX; best.block = make_uint2(0u, 0u);
+        if (TYPE == 1) {
+          cluster_fit<3>(sc, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, best);
+          if (disabled == 0u)
+            cluster_fit<4>(sc, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, best);
+        } else {
+          cluster_fit<4>(sc, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, best);
+        }
+        if (lane == 0) {
+          uint32_t* dstColour = T.out + 1 + kWords * (warp * 32 + slot) + (TYPE == 1 ? 0 : 2);
+          dstColour[0] = best.block.x; dstColour[1] = best.block.y;
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- write the record: u16 w, u16 h, blocks -------------------------------------------------
+    {
+      uint32_t* dst = reinterpret_cast<uint32_t*>(out + (size_t)tile * outStride);
+      const int words = 1 + kWords * nblocks;
+      for (int v = tid; v < words; v += kThreads) dst[v] = T.out[v];
+    }
+    __syncthreads();
+  }
+}
+
+// Colors::palToARGB for full tiles: pixel p of tile t -> B,G,R,A.
+__global__ void __launch_bounds__(kThreads)
+pal_to_argb_kernel(const uint8_t* __restrict__ tiles, int ntiles, uint32_t* __restrict__ bgra)
+{
+  __shared__ uint32_t palette[256];
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const uint8_t* rec = tiles + (size_t)tile * kTileRecord;
+    palette[threadIdx.x] = __ldg(reinterpret_cast<const uint32_t*>(rec) + threadIdx.x);
+    __syncthreads();
+    const bool keyed = palette[0] == 0x0000ff00u;
+    const uint4* idx = reinterpret_cast<const uint4*>(rec + kPaletteBytes);
+    uint4* dst = reinterpret_cast<uint4*>(bgra + (size_t)tile * 4096);
+    const uint4 v = __ldg(idx + threadIdx.x);                 // 16 indices per thread
+    const uint32_t words[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint4 o;
+      uint32_t* op = &o.x;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const uint32_t i = (words[q] >> (8 * b)) & 255u;
+        op[b] = (i == 0u && keyed) ? 0u : ((palette[i] & 0x00ffffffu) | 0xff000000u);
+      }
+      dst[threadIdx.x * 4 + q] = o;
+    }
+    __syncthreads();
+  }
+}
+
+// FP32 pipe probe: 8 independent chains per thread, no memory traffic.
+template <bool FUSED>
+__global__ void __launch_bounds__(256) fp32_probe_kernel(float* out, int iters, float seed)
+{
+  float a[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) a[c] = seed + 0.001f * (float)(threadIdx.x + c);
+  const float m = 1.0f + 1e-7f, b = 1e-9f;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      if (FUSED) a[c] = fmaf(a[c], m, b);
+      else { a[c] = a[c] * m; a[c] = a[c] + b; }
+    }
+  }
+  float s = 0.0f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) s += a[c];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// ================================================================================================
+// host: read-only tables
+// ================================================================================================
+// SingleColourFit lookups by the squishgen rule: each (start,end) pair, in
+// lexicographic order, claims the 8-bit values it reproduces exactly; unclaimed targets inherit
+// from the nearest claimed neighbour one step per sweep.
+static void make_single_table(uint8_t (*table)[2][4], int bits, int colours)
+{
+  int start[256][2], end[256][2], error[256][2];
+  for (int t = 0; t < 256; ++t)
+    for (int k = 0; k < 2; ++k) { start[t][k] = end[t][k] = 0; error[t][k] = 255; }
+  const int levels = 1 << bits;
+  for (int s = 0; s < levels; ++s)
+    for (int e = 0; e < levels; ++e) {
+      const int a = (s << (8 - bits)) | (s >> (2 * bits - 8));
+      const int b = (e << (8 - bits)) | (e >> (2 * bits - 8));
+      const int code[2] = { a, colours == 3 ? (a + b) / 2 : (2 * a + b) / 3 };
+      for (int k = 0; k < 2; ++k)
+        if (error[code[k]][k] != 0) { start[code[k]][k] = s; end[code[k]][k] = e; error[code[k]][k] = 0; }
+    }
+  for (bool changed = true; changed;) {
+    changed = false;
+    for (int k = 0; k < 2; ++k)
+      for (int t = 0; t < 256; ++t) {
+        if (t < 255 && error[t][k] > error[t + 1][k] + 1) {
+          start[t][k] = start[t + 1][k]; end[t][k] = end[t + 1][k]; error[t][k] = error[t + 1][k] + 1; changed = true;
+        }
+        if (t > 0 && error[t][k] > error[t - 1][k] + 1) {
+          start[t][k] = start[t - 1][k]; end[t][k] = end[t - 1][k]; error[t][k] = error[t - 1][k] + 1; changed = true;
+        }
+      }
+  }
+  for (int t = 0; t < 256; ++t)
+    for (int k = 0; k < 2; ++k) {
+      table[t][k][0] = (uint8_t)start[t][k]; table[t][k][1] = (uint8_t)end[t][k];
+      table[t][k][2] = (uint8_t)error[t][k]; table[t][k][3] = 0;
+    }
+}
+
+static bool build_tables(DeviceTables& h)
+{
+  std::memset(&h, 0, sizeof(h));
+  make_single_table(h.single[0], 5, 3);
+  make_single_table(h.single[1], 6, 3);
+  make_single_table(h.single[2], 5, 4);
+  make_single_table(h.single[3], 6, 4);
+  // candidate partitions in the reference's loop order (App. A.6)
+  int pos = 0;
+  const int capacity = (int)(sizeof(h.cand) / sizeof(h.cand[0]));
+  for (int n = 2; n <= 16; ++n) {
+    h.off3[n] = pos;
+    for (int i = 0; i < n; ++i)
+      for (int j = (i == 0 ? 1 : i); j <= n; ++j) {
+        if (pos >= capacity) return false;
+        h.cand[pos++] = (uint32_t)(rowoff(0) + i) | ((uint32_t)(rowoff(i) + (j - i)) << 8);
+      }
+    h.cnt3[n] = pos - h.off3[n];
+    h.off4[n] = pos;
+    for (int i = 0; i < n; ++i)
+      for (int j = i; j <= n; ++j)
+        for (int k = (j == 0 ? 1 : j); k <= n; ++k) {
+          if (pos >= capacity) return false;
+          h.cand[pos++] = (uint32_t)(rowoff(0) + i) | ((uint32_t)(rowoff(i) + (j - i)) << 8) |
+                          ((uint32_t)(rowoff(j) + (k - j)) << 16);
+        }
+    h.cnt4[n] = pos - h.off4[n];
+  }
+  return true;
+}
+
+}  // namespace tcb
+
+// ================================================================================================
+// host: context + C ABI
+// ================================================================================================
+using namespace tcb;
+
+namespace {
+
+std::mutex g_errMutex;
+std::string g_createError;
+
+constexpr int kSlabs = 3;
+constexpr int kDefaultBatch = 8192;
+
+}  // namespace
+
+struct tcb200_ctx
+{
+  int device = 0, type = 1, quality = 9, stride = 0, capacity = 0, sms = 0;
+  bool weightAlpha = false;
+  int mode = kRange;
+  size_t smemBytes = 0;
+  cudaStream_t stream[kSlabs] = {};
+  cudaEvent_t done[kSlabs] = {};
+  bool inflight[kSlabs] = {};
+  uint8_t* dIn[kSlabs] = {}; uint16_t* dWh[kSlabs] = {}; uint8_t* dOut[kSlabs] = {};
+  uint8_t* hIn[kSlabs] = {}; uint16_t* hWh[kSlabs] = {}; uint8_t* hOut[kSlabs] = {};
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  std::atomic<long long> launches{0};
+  mutable std::string error;
+};
+
+namespace {
+
+int fail(tcb200_ctx* ctx, int code, const char* what, cudaError_t e = cudaSuccess)
+{
+  std::string msg = what;
+  if (e != cudaSuccess) { msg += ": "; msg += cudaGetErrorString(e); }
+  if (ctx) ctx->error = msg;
+  else { std::lock_guard<std::mutex> lock(g_errMutex); g_createError = msg; }
+  return code;
+}
+
+#define TCB_CUDA(ctx, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, TCB200_E_CUDA, #call, e_); } while (0)
+
+typedef void (*KernelFn)(const uint8_t*, const uint16_t*, int, uint8_t*, int);
+
+KernelFn select_kernel(int type, bool weightAlpha, int mode)
+{
+#define TCB_PICK(T) \
+  if (type == T) { \
+    if (mode == kRange) return encode_tiles_kernel<T, false, kRange>; \
+    if (mode == kCluster) return weightAlpha ? encode_tiles_kernel<T, true, kCluster> : encode_tiles_kernel<T, false, kCluster>; \
+    return weightAlpha ? encode_tiles_kernel<T, true, kIterative> : encode_tiles_kernel<T, false, kIterative>; \
+  }
+  TCB_PICK(1) TCB_PICK(2) TCB_PICK(3)
+#undef TCB_PICK
+  return nullptr;
+}
+
+int launch_encode(tcb200_ctx* ctx, const uint8_t* dTiles, const uint16_t* dWh, int n, uint8_t* dOut, cudaStream_t stream)
+{
+  if (n <= 0) return TCB200_OK;
+  KernelFn fn = select_kernel(ctx->type, ctx->weightAlpha, ctx->mode);
+  fn<<<n, kThreads, ctx->smemBytes, stream>>>(dTiles, dWh, n, dOut, ctx->stride);
+  ctx->launches.fetch_add(1);
+  TCB_CUDA(ctx, cudaGetLastError());
+  return TCB200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tcb200_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int tcb200_record_size(int type, int width, int height)
+{
+  if (width <= 0 || height <= 0 || width > 64 || height > 64) return 0;
+  const int blocks = (((width + 3) & ~3) * ((height + 3) & ~3)) >> 4;
+  if (type == 1) return (blocks << 3) + 4;
+  if (type == 2 || type == 3) return (blocks << 4) + 4;
+  return 0;
+}
+
+tcb200_ctx* tcb200_create(int device, int type, int quality, int max_batch_tiles)
+{
+  if (type < 1 || type > 3 || quality < 0 || quality > 9 || max_batch_tiles < 0) {
+    fail(nullptr, TCB200_E_ARG, "tcb200_create: type must be 1..3, quality 0..9, max_batch_tiles >= 0");
+    return nullptr;
+  }
+  int count = tcb200_device_count();
+  if (count <= 0 || device < 0 || device >= count) {
+    fail(nullptr, TCB200_E_NODEVICE, "tcb200_create: no usable CUDA device (this library has no CPU fallback)");
+    return nullptr;
+  }
+  tcb200_ctx* ctx = new (std::nothrow) tcb200_ctx();
+  if (!ctx) { fail(nullptr, TCB200_E_NOMEM, "tcb200_create: out of memory"); return nullptr; }
+  ctx->device = device; ctx->type = type; ctx->quality = quality;
+  ctx->stride = tcb200_record_size(type, 64, 64);
+  ctx->capacity = max_batch_tiles > 0 ? max_batch_tiles : kDefaultBatch;
+  // ConverterDxt::getFlags (converter_dxt.cpp:191-208)
+  ctx->mode = quality <= 2 ? kRange : (quality <= 6 ? kCluster : kIterative);
+  ctx->weightAlpha = quality >= 5;
+  // kWeightColourByAlpha changes nothing for BC1 (alpha < 128 pixels leave the set, the rest weigh 256/256)
+  if (type == 1) ctx->weightAlpha = false;
+
+  auto bail = [&](const char* what, cudaError_t e) -> tcb200_ctx* {
+    fail(nullptr, TCB200_E_CUDA, what, e);
+    tcb200_destroy(ctx);
+    return nullptr;
+  };
+  cudaError_t e;
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
+  ctx->sms = prop.multiProcessorCount;
+
+  static DeviceTables hostTables;   // ~30 KB, built once
+  static std::once_flag once;
+  static bool tablesOk = false;
+  std::call_once(once, [] { tablesOk = build_tables(hostTables); });
+  if (!tablesOk) { fail(nullptr, TCB200_E_ARG, "internal: candidate table overflow"); tcb200_destroy(ctx); return nullptr; }
+  if ((e = cudaMemcpyToSymbol(g_tables, &hostTables, sizeof(hostTables))) != cudaSuccess) return bail("cudaMemcpyToSymbol(g_tables)", e);
+
+  ctx->smemBytes = sizeof(TileShared) + sizeof(WarpJobs) * kWarps + (ctx->mode == kRange ? 0 : sizeof(WarpScratch) * kWarps);
+  KernelFn fn = select_kernel(ctx->type, ctx->weightAlpha, ctx->mode);
+  if ((e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smemBytes)) != cudaSuccess)
+    return bail("cudaFuncSetAttribute(MaxDynamicSharedMemorySize)", e);
+
+  for (int s = 0; s < kSlabs; ++s) {
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream[s], cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->done[s], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaMalloc(&ctx->dIn[s], (size_t)ctx->capacity * kTileRecord)) != cudaSuccess) return bail("cudaMalloc(input)", e);
+    if ((e = cudaMalloc(&ctx->dWh[s], (size_t)ctx->capacity * 4)) != cudaSuccess) return bail("cudaMalloc(sizes)", e);
+    if ((e = cudaMalloc(&ctx->dOut[s], (size_t)ctx->capacity * ctx->stride)) != cudaSuccess) return bail("cudaMalloc(output)", e);
+  }
+  if ((e = cudaEventCreate(&ctx->t0)) != cudaSuccess) return bail("cudaEventCreate", e);
+  if ((e = cudaEventCreate(&ctx->t1)) != cudaSuccess) return bail("cudaEventCreate", e);
+  return ctx;
+}
+
+void tcb200_destroy(tcb200_ctx* ctx)
+{
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  for (int s = 0; s < kSlabs; ++s) {
+    if (ctx->stream[s]) { cudaStreamSynchronize(ctx->stream[s]); cudaStreamDestroy(ctx->stream[s]); }
+    if (ctx->done[s]) cudaEventDestroy(ctx->done[s]);
+    cudaFree(ctx->dIn[s]); cudaFree(ctx->dWh[s]); cudaFree(ctx->dOut[s]);
+    if (ctx->hIn[s]) cudaFreeHost(ctx->hIn[s]);
+    if (ctx->hWh[s]) cudaFreeHost(ctx->hWh[s]);
+    if (ctx->hOut[s]) cudaFreeHost(ctx->hOut[s]);
+  }
+  if (ctx->t0) cudaEventDestroy(ctx->t0);
+  if (ctx->t1) cudaEventDestroy(ctx->t1);
+  delete ctx;
+}
+
+const char* tcb200_last_error(const tcb200_ctx* ctx)
+{
+  if (ctx) return ctx->error.c_str();
+  std::lock_guard<std::mutex> lock(g_errMutex);
+  static thread_local std::string copy;
+  copy = g_createError;
+  return copy.c_str();
+}
+
+int tcb200_type(const tcb200_ctx* ctx) { return ctx ? ctx->type : 0; }
+int tcb200_quality(const tcb200_ctx* ctx) { return ctx ? ctx->quality : -1; }
+int tcb200_device(const tcb200_ctx* ctx) { return ctx ? ctx->device : -1; }
+int tcb200_record_stride(const tcb200_ctx* ctx) { return ctx ? ctx->stride : 0; }
+long long tcb200_launch_count(const tcb200_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
+
+int tcb200_encode_device(tcb200_ctx* ctx, const void* d_tiles, const void* d_wh, int n, void* d_out, void* stream)
+{
+  if (!ctx) return TCB200_E_ARG;
+  if (n < 0 || (n > 0 && (!d_tiles || !d_out))) return fail(ctx, TCB200_E_ARG, "tcb200_encode_device: bad argument");
+  TCB_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream[0];
+  return launch_encode(ctx, (const uint8_t*)d_tiles, (const uint16_t*)d_wh, n, (uint8_t*)d_out, s);
+}
+
+int tcb200_encode(tcb200_ctx* ctx, const uint8_t* tiles, const uint16_t* wh, int n, uint8_t* out)
+{
+  if (!ctx) return TCB200_E_ARG;
+  if (n < 0 || (n > 0 && (!tiles || !out))) return fail(ctx, TCB200_E_ARG, "tcb200_encode: bad argument");
+  if (wh) {
+    for (int i = 0; i < n; ++i)
+      if (wh[2 * i] == 0 || wh[2 * i] > 64 || wh[2 * i + 1] == 0 || wh[2 * i + 1] > 64)
+        return fail(ctx, TCB200_E_ARG, "tcb200_encode: tile dimensions must be 1..64");
+  }
+  TCB_CUDA(ctx, cudaSetDevice(ctx->device));
+  for (int s = 0; s < kSlabs; ++s)
+    if (ctx->inflight[s]) return fail(ctx, TCB200_E_ARG, "tcb200_encode: slabs are in flight; wait for them first");
+  // chunks rotate over the device buffers; stream order makes reuse of a buffer safe
+  int chunk = 0;
+  for (int first = 0; first < n; first += ctx->capacity, ++chunk) {
+    const int s = chunk % kSlabs;
+    const int m = (n - first < ctx->capacity) ? n - first : ctx->capacity;
+    cudaStream_t st = ctx->stream[s];
+    TCB_CUDA(ctx, cudaMemcpyAsync(ctx->dIn[s], tiles + (size_t)first * kTileRecord, (size_t)m * kTileRecord, cudaMemcpyHostToDevice, st));
+    if (wh) TCB_CUDA(ctx, cudaMemcpyAsync(ctx->dWh[s], wh + (size_t)first * 2, (size_t)m * 4, cudaMemcpyHostToDevice, st));
+    int rc = launch_encode(ctx, ctx->dIn[s], wh ? ctx->dWh[s] : nullptr, m, ctx->dOut[s], st);
+    if (rc != TCB200_OK) return rc;
+    TCB_CUDA(ctx, cudaMemcpyAsync(out + (size_t)first * ctx->stride, ctx->dOut[s], (size_t)m * ctx->stride, cudaMemcpyDeviceToHost, st));
+  }
+  for (int s = 0; s < kSlabs; ++s) TCB_CUDA(ctx, cudaStreamSynchronize(ctx->stream[s]));
+  return TCB200_OK;
+}
+
+int tcb200_slab_count(const tcb200_ctx* ctx) { return ctx ? kSlabs : 0; }
+int tcb200_slab_capacity(const tcb200_ctx* ctx) { return ctx ? ctx->capacity : 0; }
+
+static int ensure_slab(tcb200_ctx* ctx, int slab)
+{
+  if (!ctx) return TCB200_E_ARG;
+  if (slab < 0 || slab >= kSlabs) return fail(ctx, TCB200_E_ARG, "slab index out of range");
+  if (ctx->hIn[slab]) return TCB200_OK;
+  TCB_CUDA(ctx, cudaSetDevice(ctx->device));
+  TCB_CUDA(ctx, cudaHostAlloc((void**)&ctx->hIn[slab], (size_t)ctx->capacity * kTileRecord, cudaHostAllocDefault));
+  TCB_CUDA(ctx, cudaHostAlloc((void**)&ctx->hWh[slab], (size_t)ctx->capacity * 4, cudaHostAllocDefault));
+  TCB_CUDA(ctx, cudaHostAlloc((void**)&ctx->hOut[slab], (size_t)ctx->capacity * ctx->stride, cudaHostAllocDefault));
+  return TCB200_OK;
+}
+
+uint8_t* tcb200_slab_input(tcb200_ctx* ctx, int slab) { return ensure_slab(ctx, slab) == TCB200_OK ? ctx->hIn[slab] : nullptr; }
+uint16_t* tcb200_slab_sizes(tcb200_ctx* ctx, int slab) { return ensure_slab(ctx, slab) == TCB200_OK ? ctx->hWh[slab] : nullptr; }
+uint8_t* tcb200_slab_output(tcb200_ctx* ctx, int slab) { return ensure_slab(ctx, slab) == TCB200_OK ? ctx->hOut[slab] : nullptr; }
+
+int tcb200_slab_submit(tcb200_ctx* ctx, int slab, int n)
+{
+  int rc = ensure_slab(ctx, slab);
+  if (rc != TCB200_OK) return rc;
+  if (n < 0 || n > ctx->capacity) return fail(ctx, TCB200_E_ARG, "tcb200_slab_submit: n out of range");
+  if (ctx->inflight[slab]) return fail(ctx, TCB200_E_ARG, "tcb200_slab_submit: slab still in flight");
+  for (int i = 0; i < n; ++i) {
+    const uint16_t w = ctx->hWh[slab][2 * i], h = ctx->hWh[slab][2 * i + 1];
+    if (w == 0 || w > 64 || h == 0 || h > 64) return fail(ctx, TCB200_E_ARG, "tcb200_slab_submit: tile dimensions must be 1..64");
+  }
+  TCB_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream[slab];
+  TCB_CUDA(ctx, cudaMemcpyAsync(ctx->dIn[slab], ctx->hIn[slab], (size_t)n * kTileRecord, cudaMemcpyHostToDevice, st));
+  TCB_CUDA(ctx, cudaMemcpyAsync(ctx->dWh[slab], ctx->hWh[slab], (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  rc = launch_encode(ctx, ctx->dIn[slab], ctx->dWh[slab], n, ctx->dOut[slab], st);
+  if (rc != TCB200_OK) return rc;
+  TCB_CUDA(ctx, cudaMemcpyAsync(ctx->hOut[slab], ctx->dOut[slab], (size_t)n * ctx->stride, cudaMemcpyDeviceToHost, st));
+  TCB_CUDA(ctx, cudaEventRecord(ctx->done[slab], st));
+  ctx->inflight[slab] = true;
+  return TCB200_OK;
+}
+
+int tcb200_slab_wait(tcb200_ctx* ctx, int slab)
+{
+  if (!ctx) return TCB200_E_ARG;
+  if (slab < 0 || slab >= kSlabs) return fail(ctx, TCB200_E_ARG, "slab index out of range");
+  if (!ctx->inflight[slab]) return TCB200_OK;
+  TCB_CUDA(ctx, cudaEventSynchronize(ctx->done[slab]));
+  ctx->inflight[slab] = false;
+  return TCB200_OK;
+}
+
+int tcb200_slab_ready(tcb200_ctx* ctx, int slab)
+{
+  if (!ctx) return TCB200_E_ARG;
+  if (slab < 0 || slab >= kSlabs) return fail(ctx, TCB200_E_ARG, "slab index out of range");
+  if (!ctx->inflight[slab]) return 1;
+  cudaError_t e = cudaEventQuery(ctx->done[slab]);
+  if (e == cudaSuccess) { ctx->inflight[slab] = false; return 1; }
+  if (e == cudaErrorNotReady) return 0;
+  return fail(ctx, TCB200_E_CUDA, "cudaEventQuery", e);
+}
+
+void* tcb200_host_alloc(size_t bytes)
+{
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+void tcb200_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int tcb200_pal_to_argb(tcb200_ctx* ctx, const uint8_t* tiles, int n, uint8_t* bgra)
+{
+  if (!ctx) return TCB200_E_ARG;
+  if (n < 0 || (n > 0 && (!tiles || !bgra))) return fail(ctx, TCB200_E_ARG, "tcb200_pal_to_argb: bad argument");
+  TCB_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream[0];
+  uint32_t* dPix = nullptr;
+  for (int first = 0; first < n; first += ctx->capacity) {
+    const int m = (n - first < ctx->capacity) ? n - first : ctx->capacity;
+    if (!dPix) TCB_CUDA(ctx, cudaMalloc(&dPix, (size_t)(n < ctx->capacity ? n : ctx->capacity) * 4096 * 4));
+    cudaError_t e = cudaMemcpyAsync(ctx->dIn[0], tiles + (size_t)first * kTileRecord, (size_t)m * kTileRecord, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+      pal_to_argb_kernel<<<m, kThreads, 0, st>>>(ctx->dIn[0], m, dPix);
+      ctx->launches.fetch_add(1);
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(bgra + (size_t)first * 4096 * 4, dPix, (size_t)m * 4096 * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { cudaFree(dPix); return fail(ctx, TCB200_E_CUDA, "tcb200_pal_to_argb", e); }
+  }
+  cudaFree(dPix);
+  return TCB200_OK;
+}
+
+float tcb200_time_kernel_ms(tcb200_ctx* ctx, const void* d_tiles, const void* d_wh, int n, void* d_out, int reps)
+{
+  if (!ctx || reps <= 0 || n <= 0 || !d_tiles || !d_out) return (float)TCB200_E_ARG;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return (float)TCB200_E_CUDA;
+  cudaStream_t st = ctx->stream[0];
+  if (cudaEventRecord(ctx->t0, st) != cudaSuccess) return (float)TCB200_E_CUDA;
+  for (int r = 0; r < reps; ++r)
+    if (launch_encode(ctx, (const uint8_t*)d_tiles, (const uint16_t*)d_wh, n, (uint8_t*)d_out, st) != TCB200_OK) return (float)TCB200_E_CUDA;
+  if (cudaEventRecord(ctx->t1, st) != cudaSuccess) return (float)TCB200_E_CUDA;
+  if (cudaEventSynchronize(ctx->t1) != cudaSuccess) { fail(ctx, TCB200_E_CUDA, "cudaEventSynchronize", cudaGetLastError()); return (float)TCB200_E_CUDA; }
+  float ms = 0.0f;
+  if (cudaEventElapsedTime(&ms, ctx->t0, ctx->t1) != cudaSuccess) return (float)TCB200_E_CUDA;
+  return ms / (float)reps;
+}
+
+double tcb200_fp32_peak(tcb200_ctx* ctx, int fused)
+{
+  if (!ctx) return (double)TCB200_E_ARG;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return (double)TCB200_E_CUDA;
+  const int grid = ctx->sms * 8, iters = 1 << 16;
+  float* dOut = nullptr;
+  if (cudaMalloc(&dOut, (size_t)grid * 256 * sizeof(float)) != cudaSuccess) return (double)TCB200_E_NOMEM;
+  cudaStream_t st = ctx->stream[0];
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {          // rep 0 warms the clocks up
+    cudaEventRecord(ctx->t0, st);
+    if (fused) fp32_probe_kernel<true><<<grid, 256, 0, st>>>(dOut, iters, 1.0f);
+    else fp32_probe_kernel<false><<<grid, 256, 0, st>>>(dOut, iters, 1.0f);
+    ctx->launches.fetch_add(1);
+    cudaEventRecord(ctx->t1, st);
+    if (cudaEventSynchronize(ctx->t1) != cudaSuccess) { cudaFree(dOut); return (double)TCB200_E_CUDA; }
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, ctx->t0, ctx->t1);
+    const double instrLanes = (double)grid * 256.0 * (double)iters * 8.0 * (fused ? 1.0 : 2.0);
+    const double rate = instrLanes / (ms * 1e-3);
+    if (rep > 0 && rate > best) best = rate;
+  }
+  cudaFree(dOut);
+  return best;
+}
+
+}  // extern "C"

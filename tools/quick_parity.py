@@ -1,0 +1,37 @@
+"""Quick GPU-vs-oracle parity sweep (development aid; the real tests live in tests/)."""
+import sys, time, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from tileconv_b200 import Encoder, synth
+from oracle import pyoracle
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+    sets = {"S-U": synth.uniform_tiles(n), "S-G": synth.smooth_tiles(n), "S-K": synth.keyed_tiles(n)}
+    rag, wh = synth.ragged_tiles(n)
+    bad = 0
+    for t in (1, 2, 3):
+        for q in (0, 2, 3, 5, 7, 9):
+            with Encoder(t, q) as enc:
+                for name, tiles in sets.items():
+                    t0 = time.time(); got = enc.encode(tiles); dt = time.time() - t0
+                    want = pyoracle.encode_tiles(tiles, t, q, threads=8)
+                    bs = 8 if t == 1 else 16
+                    g = got[:, 4:].reshape(n, 256, bs); w_ = want[:, 4:].reshape(n, 256, bs)
+                    diff = (g != w_).any(axis=2).sum()
+                    hdr = (got[:, :4] != want[:, :4]).any()
+                    print(f"type {t} q {q} {name}: blocks differing {diff}/{n*256} header_bad {hdr} gpu {dt*1e3:.1f} ms")
+                    bad += int(diff) + int(hdr)
+                got = enc.encode(rag, wh)
+                want = pyoracle.encode_tiles_wh(rag, wh, t, q)
+                nd = 0
+                for i in range(n):
+                    sz = pyoracle.record_size(t, int(wh[i, 0]), int(wh[i, 1]))
+                    nd += int((got[i, :sz] != want[i, :sz]).any())
+                print(f"type {t} q {q} ragged: tiles differing {nd}/{n}")
+                bad += nd
+    print("TOTAL BAD", bad)
+    return 1 if bad else 0
+
+if __name__ == "__main__":
+    sys.exit(main())
