@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the TIS -> TBC encode hot path on B200, one JSON line on stdout.
+
+Workload (config.workload): BASELINE.json configs[4] -- the BC1 `-q 9` throughput sweep on synthetic
+64x64 tiles (half S-U, half S-G, tileconv_b200/synth.py), every tile byte-distinct (palette
+rotation).  One step = one pass of the hot path over one batch of `--batch` tiles per GPU; with N
+GPUs the tile-index range is sharded N ways with no collective (weak scaling: each rank encodes its
+own `--batch` tiles per step).
+
+  value        tiles/s, kernel only, tiles resident in HBM, CUDA events on the launching stream,
+               max over ranks.  Inputs (batch x 5120 B) are larger than the 126 MB L2.
+  e2e          tiles/s through the C ABI tcb200_encode(): pinned HOST buffers in, pinned HOST buffers
+               out, H2D + kernels + D2H inside the timed region.
+  roofline     FP32-ALU roofline of the dominant kernel (the path is ALU-bound, not a contraction):
+               algorithmic flops = candidates the ORACLE evaluated on the same tiles x the per-
+               candidate op counts of SURVEY.md s8d (160 / 138) + the fixed per-block term;
+               peak = FFMA-loop rate measured live on this GPU.  `hbm` sub-object: algorithmic
+               bytes (7172 B/tile BC1) over the same kernel time against MEASURED_PEAKS.json.
+  cpu_baseline the reference's own per-tile CPU path (oracle/_ref: reference glue + restated squish)
+               on all host cores, bounded sample, rank 0 only.
+
+`--impl reference` times that CPU path alone (the reference arm).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+F4_OPS = 160       # FP32 operations per 4-colour candidate
+F3_OPS = 138       # per 3-colour candidate
+POOL_TILES = 4096  # distinct synthetic tiles; a batch is palette-rotated copies of the pool
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--type", type=int, default=1)
+    ap.add_argument("--quality", type=int, default=9)
+    ap.add_argument("--batch", type=int, default=65536, help="tiles per GPU per step")
+    ap.add_argument("--cpu-sample", type=int, default=2048, help="tiles in the CPU baseline sample")
+    ap.add_argument("--no-modes", action="store_true", help="skip the BC3/-q2 side measurements")
+    return ap.parse_args()
+
+
+def make_pool():
+    from tileconv_b200 import synth
+    return synth.mixed_tiles(POOL_TILES, seed=777)
+
+
+def fill_batch(dst: np.ndarray, pool: np.ndarray, first_global_tile: int) -> None:
+    """dst[(k*POOL + i)] = pool[i] with its palette rotated by a shift derived from the global copy
+    number, so no two tiles of the whole job are byte-identical while every copy encodes to the
+    same blocks as its pool tile."""
+    from tileconv_b200 import synth
+    n = dst.shape[0]
+    p = pool.shape[0]
+    for lo in range(0, n, p):
+        m = min(p, n - lo)
+        copy = (first_global_tile + lo) // p
+        shift = copy % 256
+        dst[lo:lo + m] = synth.rotate_palettes(pool[:m], shift) if shift else pool[:m]
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons while the timed region runs."""
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 7:
+                self.samples.append(parts)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for p in self.samples:
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        # samples under load: drop the idle ones (clock well below the rest) if any load samples exist
+        load = [c for c in sm if c > 0.5 * max(sm)] if sm else []
+        return {"sm_mhz": statistics.median(load) if load else None,
+                "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def cpu_reference_rate(pool: np.ndarray, sample: int, type_: int, quality: int, repeats: int = 1):
+    """Times the reference's CPU path on all host cores over `sample` tiles.  Returns
+    (tiles_per_s, cores, kind, counters_per_tile)."""
+    from oracle import pyoracle
+    cores = os.cpu_count() or 1
+    tiles = pool[:sample]
+    best = None
+    counters = None
+    use_ref = pyoracle.reference() is not None
+    for _ in range(repeats):
+        if use_ref:
+            pyoracle.ref_totals_reset()
+            t0 = time.perf_counter()
+            pyoracle.ref_encode_tiles(tiles, type_, quality, cores)
+            dt = time.perf_counter() - t0
+            c = pyoracle.ref_totals()
+        else:
+            pyoracle.totals_reset()
+            t0 = time.perf_counter()
+            pyoracle.encode_tiles(tiles, type_, quality, cores)
+            dt = time.perf_counter() - t0
+            c = pyoracle.totals()
+        if best is None or dt < best:
+            best, counters = dt, c
+    per_tile = {k: v / len(tiles) for k, v in counters.items()}
+    return len(tiles) / best, cores, ("reference" if use_ref else "port"), per_tile
+
+
+def flops_per_tile(per_tile: dict) -> float:
+    """W = C3*138 + C4*160 + F_fixed, F_fixed(n) ~ 30 n + 8*27 per cluster block."""
+    return (per_tile["cand3"] * F3_OPS + per_tile["cand4"] * F4_OPS
+            + 30.0 * per_tile["points"] + 8 * 27 * per_tile["cluster_blocks"])
+
+
+def workload_name(type_: int, quality: int, batch: int) -> str:
+    return (f"BASELINE configs[4]: synthetic 64x64 tiles (50% S-U uniform, 50% S-G smooth, palette-rotated copies of a "
+            f"{POOL_TILES}-tile pool) -> TBC records, BC{type_} -q {quality}, {batch} tiles per GPU per step, tile-range sharding")
+
+
+def run_reference(args, rank: int, world: int) -> int:
+    if rank != 0:
+        return 0
+    pool = make_pool()
+    sample = min(args.cpu_sample, POOL_TILES)
+    rates = []
+    kind, cores = "port", os.cpu_count() or 1
+    for step in range(args.warmup + args.steps):
+        rate, cores, kind, _ = cpu_reference_rate(pool, sample, args.type, args.quality)
+        if step >= args.warmup:
+            rates.append(rate)
+    value = len(rates) * sample / sum(sample / r for r in rates)
+    line = {
+        "impl": "reference",
+        "metric": f"tiles_per_s_bc{args.type}_q{args.quality}", "value": value, "unit": "tiles/s",
+        "mpix_per_s": value * 4096 / 1e6,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * sample / value, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.type, args.quality, args.batch),
+                   "step": f"one pass over a bounded sample of {sample} tiles of that workload on all host cores"},
+        "cpu_baseline": {"value": value, "unit": "tiles/s", "cores": cores, "kind": kind,
+                         "sample": f"{sample} tiles (first of the {POOL_TILES}-tile pool), {cores} std::threads, static partition, "
+                                   "each looping the reference's TileData::encode with -u semantics (BASELINE.md baseline B); "
+                                   "squish = restated oracle (libsquish is not vendored by the reference)"},
+        "e2e": {"value": value, "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main() -> int:
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    from tileconv_b200 import Encoder, capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    B = args.batch
+    pool = make_pool()
+    enc = Encoder(args.type, args.quality, device=local_rank, max_batch_tiles=8192)
+    stride = enc.stride
+
+    # ---- this rank's shard: global tiles [rank*B, (rank+1)*B) in pinned host memory ------------
+    h_in = capi.PinnedBuffer(B * capi.TILE_RECORD)
+    h_out = capi.PinnedBuffer(B * stride)
+    tiles = h_in.array.reshape(B, capi.TILE_RECORD)
+    fill_batch(tiles, pool, rank * B)
+
+    d_in = torch.empty(B * capi.TILE_RECORD, dtype=torch.uint8, device="cuda")
+    d_out = torch.zeros(B * stride, dtype=torch.uint8, device="cuda")
+    d_in.copy_(torch.from_numpy(tiles.reshape(-1)), non_blocking=False)
+    torch.cuda.synchronize()
+
+    # ---- kernel-only: W warm-up steps, then exactly K timed steps -----------------------------
+    for _ in range(args.warmup):
+        enc.encode_device(d_in.data_ptr(), None, B, d_out.data_ptr())
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = enc.launch_count()
+    t_wall0 = time.perf_counter()
+    ms_kernel = enc.time_kernel_ms(d_in.data_ptr(), None, B, d_out.data_ptr(), args.steps)   # CUDA events on the launch stream
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = enc.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = max_over_ranks(ms_kernel)
+    value = world * B / (ms_step * 1e-3)
+
+    # the device result of the timed run must be the real thing: spot-check it on rank 0 below
+    dev_result = d_out.cpu().numpy().reshape(B, stride)
+
+    # ---- end to end through the C ABI: pinned host in -> pinned host out -----------------------
+    for _ in range(min(args.warmup, 2)):
+        enc.encode_ptr(h_in.ptr, None, B, h_out.ptr)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        enc.encode_ptr(h_in.ptr, None, B, h_out.ptr)
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    e2e_s = max_over_ranks(e2e_s)
+    e2e_value = world * B / e2e_s
+    host_result = h_out.array.reshape(B, stride)
+    same = bool(np.array_equal(host_result, dev_result))
+
+    # ---- side measurements: the other modes the metric names (kernel only, fewer steps) ---------
+    modes = {}
+    if not args.no_modes:
+        for (t_, q_) in ((1, 2), (3, 9), (3, 2)):
+            if (t_, q_) == (args.type, args.quality):
+                continue
+            with Encoder(t_, q_, device=local_rank, max_batch_tiles=1024) as e2:
+                d_o2 = torch.zeros(B * e2.stride, dtype=torch.uint8, device="cuda")
+                e2.encode_device(d_in.data_ptr(), None, B, d_o2.data_ptr())
+                torch.cuda.synchronize()
+                ms2 = e2.time_kernel_ms(d_in.data_ptr(), None, B, d_o2.data_ptr(), 2)
+                ms2 = max_over_ranks(ms2)
+                modes[f"bc{t_}_q{q_}"] = {"tiles_per_s": world * B / (ms2 * 1e-3), "ms_per_step": ms2}
+                del d_o2
+
+    # ---- FP32 peaks measured live (rank 0's GPU) ------------------------------------------------
+    peak_fused = enc.fp32_peak(True) * 2.0      # FLOP/s, an FFMA counts 2
+    peak_unfused = enc.fp32_peak(False)         # FLOP/s of separate FMUL / FADD
+
+    if rank != 0:
+        barrier()
+        enc.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- rank 0: CPU baseline, parity spot check, roofline --------------------------------------
+    from oracle import pyoracle
+    sample = min(args.cpu_sample, POOL_TILES)
+    cpu_rate, cores, kind, per_tile = cpu_reference_rate(pool, sample, args.type, args.quality)
+    # parity of the measured outputs: the first `sample` tiles of the batch are pool tiles (copy 0)
+    want = pyoracle.encode_tiles(pool[:256], args.type, args.quality, threads=cores)
+    parity_ok = bool(np.array_equal(dev_result[:256], want)) if rank * B == 0 else None
+
+    flops_tile = flops_per_tile(per_tile)
+    achieved_tflops = flops_tile * (B / (ms_kernel * 1e-3)) / 1e12          # this rank's kernel
+    bytes_tile = capi.TILE_RECORD + stride
+    achieved_gbs = bytes_tile * (B / (ms_kernel * 1e-3)) / 1e9
+    hbm_peak, hbm_src = 6650.0, "fallback"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            hbm_peak, hbm_src = float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        pass
+
+    line = {
+        "metric": f"tiles_per_s_bc{args.type}_q{args.quality}", "value": value, "unit": "tiles/s",
+        "mpix_per_s": value * 4096 / 1e6,
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.type, args.quality, B),
+                   "l2": f"inputs larger than L2: {B * capi.TILE_RECORD / 1e6:.0f} MB read per step per GPU",
+                   "timing": "CUDA events on the launching stream around K back-to-back launches, max over ranks"},
+        "e2e": {"value": e2e_value, "unit": "tiles/s", "h2d_bytes_per_step": B * capi.TILE_RECORD, "d2h_bytes_per_step": B * stride,
+                "ms_per_step": e2e_s * 1e3, "path": "tcb200_encode(): pinned host -> H2D -> kernel -> D2H -> pinned host, 8192-tile chunks on 3 streams",
+                "matches_device_result": same},
+        "gpu_launches": int(launches),
+        "wall_ms_per_step": 1e3 * t_wall / args.steps,
+        "clocks": clocks,
+        "roofline": {"bound": "fp32_alu", "achieved": achieved_tflops, "peak": peak_fused / 1e12, "unit": "TFLOP/s",
+                     "frac": achieved_tflops / (peak_fused / 1e12), "traffic": None,
+                     "peak_source": "FFMA loop measured live by tcb200_fp32_peak (an FFMA = 2 flops)",
+                     "peak_unfused": peak_unfused / 1e12,
+                     "frac_of_unfused": achieved_tflops / (peak_unfused / 1e12),
+                     "note": "bit-exactness forbids mul+add fusion, so the attainable ceiling is peak_unfused (separate FMUL/FADD)",
+                     "flops_per_tile": flops_tile,
+                     "candidates_per_tile": {"c3": per_tile["cand3"], "c4": per_tile["cand4"]},
+                     "hbm": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
+                             "bytes_per_tile": bytes_tile, "peak_source": f"MEASURED_PEAKS.json ({hbm_src})"}},
+        "cpu_baseline": {"value": cpu_rate, "unit": "tiles/s", "cores": cores, "kind": kind,
+                         "sample": f"{sample} pool tiles, {cores} threads over the reference's TileData::encode (-u), restated squish"},
+        "parity_spot_check": parity_ok,
+        "modes": modes,
+    }
+    print(json.dumps(line), flush=True)
+    barrier()
+    enc.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

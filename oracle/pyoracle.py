@@ -142,6 +142,16 @@ def totals() -> dict:
     return c.as_dict()
 
 
+def ref_totals_reset() -> None:
+    reference().tcref_totals_reset()
+
+
+def ref_totals() -> dict:
+    c = Counters()
+    reference().tcref_totals_get(ctypes.byref(c))
+    return c.as_dict()
+
+
 def single_colour_table(bits: int, colours: int) -> np.ndarray:
     out = np.zeros(256 * 6, np.uint8)
     oracle().squish_oracle_single_colour_table(bits, colours, _p(out))

@@ -9,13 +9,29 @@
  * reference's pool workers run per tile (tilethreadpool_posix.cpp:119-145). */
 #include <cstdint>
 #include <cstring>
+#include <mutex>
 #include <thread>
 #include <vector>
+#include <squish.h>
 #include "converter.h"
 #include "options.h"
 #include "tiledata.h"
 
 namespace {
+
+std::mutex g_totalsMutex;
+SquishOracleCounters g_totals;   /* candidates the restated squish evaluated, summed over workers */
+
+void addTotals()
+{
+  SquishOracleCounters c;
+  squish_oracle_counters_get(&c);
+  std::lock_guard<std::mutex> lock(g_totalsMutex);
+  g_totals.blocks += c.blocks; g_totals.single_blocks += c.single_blocks;
+  g_totals.range_blocks += c.range_blocks; g_totals.cluster_blocks += c.cluster_blocks;
+  g_totals.cand3 += c.cand3; g_totals.cand4 += c.cand4;
+  g_totals.sweeps3 += c.sweeps3; g_totals.sweeps4 += c.sweeps4; g_totals.points += c.points;
+}
 
 tc::Encoding encodingOf(int type)
 {
@@ -89,11 +105,13 @@ int tcref_encode_tiles(const uint8_t* tiles, int n, int type, int quality, uint8
   if (threads > n) threads = n > 0 ? n : 1;
   std::vector<int> failed((size_t)threads, 0);
   auto work = [&](int t) {
+    squish_oracle_counters_reset();
     int lo = (int)((long long)n * t / threads), hi = (int)((long long)n * (t + 1) / threads);
     for (int i = lo; i < hi; ++i)
       if (encodeOne(options, i, tiles + (size_t)i * 5120, tiles + (size_t)i * 5120 + 1024, 64, 64,
                     out + (size_t)i * record, record) != record)
         ++failed[(size_t)t];
+    addTotals();
   };
   if (threads == 1) { work(0); return failed[0]; }
   std::vector<std::thread> pool;
@@ -103,5 +121,8 @@ int tcref_encode_tiles(const uint8_t* tiles, int n, int type, int quality, uint8
   for (int f : failed) total += f;
   return total;
 }
+
+void tcref_totals_reset(void) { std::lock_guard<std::mutex> lock(g_totalsMutex); std::memset(&g_totals, 0, sizeof(g_totals)); }
+void tcref_totals_get(SquishOracleCounters* out) { std::lock_guard<std::mutex> lock(g_totalsMutex); *out = g_totals; }
 
 }  // extern "C"

@@ -1,0 +1,100 @@
+"""Size-independent properties of the oracle (there are no reference tests to borrow):
+decode round trips through the restated reference decoder, monotone quality, degenerate blocks."""
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+from tileconv_b200 import synth
+
+K_DXT1, K_DXT3, K_DXT5 = 1, 2, 4
+K_CLUSTER, K_RANGE, K_WEIGHT, K_ITER = 8, 16, 128, 256
+
+
+def tile_rmse(oracle, tiles, records, type_):
+    """Per-tile RGB RMSE (8-bit units) of decode(records) against the expanded source pixels."""
+    out = []
+    for t, rec in zip(tiles, records):
+        src = oracle.pal_to_argb(t[1024:], t[:1024]).reshape(64, 64, 4).astype(np.float64)
+        dec = oracle.decode_tile(rec, type_).astype(np.float64)
+        opaque = src[:, :, 3] > 0
+        if not opaque.any():
+            out.append(0.0); continue
+        d = (src[:, :, :3] - dec[:, :, :3])[opaque]
+        out.append(float(np.sqrt((d ** 2).mean())))
+    return np.array(out)
+
+
+@pytest.mark.parametrize("type_", (1, 3))
+def test_quality_is_monotone_on_average(oracle, type_):
+    tiles = np.concatenate([synth.uniform_tiles(2, 31), synth.smooth_tiles(3, 32)])
+    rmse = {q: tile_rmse(oracle, tiles, oracle.encode_tiles(tiles, type_, q, threads=4), type_).mean() for q in (2, 4, 9)}
+    assert rmse[9] <= rmse[4] + 1e-9 <= rmse[2] + 1e-9
+    assert rmse[9] < 40.0           # sanity: a broken encoder is far above this even on noise
+
+
+def test_quality_levels_inside_a_class_are_identical(oracle):
+    tiles = np.concatenate([synth.smooth_tiles(1, 33), synth.keyed_tiles(1, 34)])
+    for t in (1, 2, 3):
+        for group in ((0, 1, 2), (3, 4), (5, 6), (7, 8, 9)):
+            ref = oracle.encode_tiles(tiles, t, group[0])
+            for q in group[1:]:
+                assert np.array_equal(ref, oracle.encode_tiles(tiles, t, q))
+    # kWeightColourByAlpha is a no-op for BC1 (binary alpha): classes {3,4} and {5,6} coincide
+    assert np.array_equal(oracle.encode_tiles(tiles, 1, 4), oracle.encode_tiles(tiles, 1, 6))
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.tuples(st.integers(0, 255), st.integers(0, 255), st.integers(0, 255)),
+       st.sampled_from([K_RANGE, K_CLUSTER, K_ITER | K_WEIGHT]))
+def test_solid_blocks_decode_within_table_error(oracle, colour, fit):
+    blk = np.array([list(colour) + [255]] * 16, np.uint8)
+    enc = oracle.compress_block(blk, K_DXT1 | fit)
+    px = oracle.decode_tile(np.concatenate([np.array([4, 0, 4, 0], np.uint8), enc]), 1)
+    t5 = oracle.single_colour_table(5, 3).astype(int); t6 = oracle.single_colour_table(6, 3).astype(int)
+    u5 = oracle.single_colour_table(5, 4).astype(int); u6 = oracle.single_colour_table(6, 4).astype(int)
+    r, g, b = colour
+    bound = [max(min(t5[r, k, 2] for k in (0, 1)), min(u5[r, k, 2] for k in (0, 1))) + 1,
+             max(min(t6[g, k, 2] for k in (0, 1)), min(u6[g, k, 2] for k in (0, 1))) + 1,
+             max(min(t5[b, k, 2] for k in (0, 1)), min(u5[b, k, 2] for k in (0, 1))) + 1]
+    assert (px[:, :, 3] == 255).all()
+    assert (px[:, :, 2] == px[0, 0, 2]).all()                      # one colour everywhere
+    for c, want in zip((2, 1, 0), (r, g, b)):                       # decoder writes B,G,R
+        assert abs(int(px[0, 0, c]) - want) <= bound[(2, 1, 0).index(c)] + 2
+
+
+@settings(max_examples=40, deadline=None)
+@given(st.integers(0, 2 ** 32 - 1))
+def test_two_colour_blocks_are_reproduced_by_cluster_fit(oracle, seed):
+    rng = np.random.default_rng(seed)
+    c0, c1 = rng.integers(0, 256, (2, 3))
+    mask = rng.random(16) < 0.5
+    blk = np.zeros((16, 4), np.uint8); blk[:, 3] = 255
+    blk[mask, :3] = c0; blk[~mask, :3] = c1
+    enc = oracle.compress_block(blk, K_DXT1 | K_ITER | K_WEIGHT)
+    px = oracle.decode_tile(np.concatenate([np.array([4, 0, 4, 0], np.uint8), enc]), 1).reshape(16, 4)
+    # endpoints are 565-quantised: each channel within 8 (5-bit) / 4 (6-bit) of the source
+    err = np.abs(px[:, [2, 1, 0]].astype(int) - blk[:, :3].astype(int))
+    assert err[:, 0].max() <= 8 and err[:, 1].max() <= 4 and err[:, 2].max() <= 8
+
+
+def test_transparent_pixels_keep_code_3_in_bc1(oracle):
+    tiles = synth.keyed_tiles(2, 35)
+    rec = oracle.encode_tiles(tiles, 1, 9)
+    for t, r in zip(tiles, rec):
+        src = oracle.pal_to_argb(t[1024:], t[:1024]).reshape(64, 64, 4)
+        dec = oracle.decode_tile(r, 1)
+        assert np.array_equal(dec[:, :, 3] == 0, src[:, :, 3] == 0)
+
+
+def test_counters_match_closed_form(oracle):
+    # n = 16 distinct colours: 151 three-colour and 967 four-colour partitions per ordering
+    rng = np.random.default_rng(7)
+    blk = np.zeros((16, 4), np.uint8); blk[:, 3] = 255
+    blk[:, :3] = rng.permutation(256)[:16, None] + np.array([0, 0, 0])
+    blk[:, 1] = rng.permutation(256)[:16]
+    oracle.oracle().squish_oracle_counters_reset()
+    oracle.compress_block(blk, K_DXT1 | K_CLUSTER)
+    from oracle.pyoracle import Counters
+    import ctypes
+    c = Counters(); oracle.oracle().squish_oracle_counters_get(ctypes.byref(c))
+    assert (c.cand3, c.cand4, c.sweeps3, c.sweeps4) == (151, 967, 1, 1)
