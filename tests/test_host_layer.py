@@ -1,0 +1,204 @@
+"""The C++ host layer (tileconv_b200/host): ConverterDxtCuda behind ConverterFactory, TileBatchQueue
+behind createThreadPool()'s interface, and the TIS/MOS -> TBC/MBC drivers.  GPU tests; expected bytes
+come from the CPU oracle and, where the reference CLI was built (oracle/_ref/tileconv_ref), from the
+reference program itself."""
+import ctypes
+import os
+import struct
+import subprocess
+import zlib
+
+import numpy as np
+import pytest
+
+from tileconv_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOSTLIB = os.path.join(ROOT, "tileconv_b200", "libtcb200_host.so")
+REF_CLI = os.path.join(ROOT, "oracle", "_ref", "tileconv_ref")
+CUDA_CLI = os.path.join(ROOT, "oracle", "_ref", "tileconv_cuda")
+TBC_ENCODE = os.path.join(ROOT, "tileconv_b200", "tbc_encode")
+
+
+def test_host_library_exports():
+    lib = ctypes.CDLL(HOSTLIB)
+    for name in ("tcbh_convert_tile", "tcbh_queue_encode", "tcbh_encode_file", "tcbh_last_error"):
+        assert hasattr(lib, name)
+
+
+@pytest.fixture(scope="module")
+def host():
+    lib = ctypes.CDLL(HOSTLIB)
+    lib.tcbh_last_error.restype = ctypes.c_char_p
+    return lib
+
+
+def p(a):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+# ---- file helpers --------------------------------------------------------------------------------
+def write_tis(path, tiles, header=True):
+    with open(path, "wb") as f:
+        if header:
+            f.write(b"TIS V1  " + struct.pack("<IIII", len(tiles), 0x1400, 0x18, 0x40))
+        f.write(tiles.tobytes())
+
+
+def make_mos(width, height, seed, compressed=False):
+    """MOS V1: header, palettes, offset table, tile data with row pitch = tile width (graphics.cpp:296-342)."""
+    cols, rows = (width + 63) // 64, (height + 63) // 64
+    n = cols * rows
+    base = synth.keyed_tiles(n, seed)
+    pal = base[:, :1024].tobytes()
+    table, data, wh, packed = [], b"", [], np.zeros((n, 5120), np.uint8)
+    for i in range(n):
+        r, c = divmod(i, cols)
+        w, h = min(64, width - c * 64), min(64, height - r * 64)
+        img = base[i, 1024:].reshape(64, 64)[:h, :w].reshape(-1)
+        table.append(len(data)); data += img.tobytes(); wh.append((w, h))
+        packed[i, :1024] = base[i, :1024]; packed[i, 1024:1024 + w * h] = img
+    mos = b"MOS V1  " + struct.pack("<HHHHII", width, height, cols, rows, 64, 24) + pal + struct.pack(f"<{n}I", *table) + data
+    if compressed:
+        mos = b"MOSCV1  " + struct.pack("<I", len(mos)) + zlib.compress(mos, 9)
+    return mos, packed, np.array(wh, np.uint16)
+
+
+def expected_stream(oracle, header, tiles, wh, type_, quality, deflate):
+    out = header
+    for i in range(len(tiles)):
+        w, h = (64, 64) if wh is None else (int(wh[i, 0]), int(wh[i, 1]))
+        rec = oracle.encode_tile(tiles[i, :1024], tiles[i, 1024:1024 + w * h], w, h, type_, quality).tobytes()
+        if deflate:
+            rec = zlib.compress(rec, 9)
+        out += struct.pack("<I", len(rec)) + rec
+    return out
+
+
+# ---- per-tile plugin surface --------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("type_,quality", ((1, 9), (2, 2), (3, 7)))
+def test_converter_plugin_single_tiles(host, oracle, type_, quality):
+    tiles, wh = synth.ragged_tiles(6, 91)
+    for i in range(len(tiles)):
+        w, h = int(wh[i, 0]), int(wh[i, 1])
+        out = np.zeros(8192, np.uint8)
+        pal, idx = tiles[i, :1024].copy(), tiles[i, 1024:].copy()      # keep the buffers alive across the call
+        n = host.tcbh_convert_tile(type_, quality, p(pal), p(idx), w, h, p(out), 8192)
+        want = oracle.encode_tile(tiles[i, :1024], tiles[i, 1024:1024 + w * h], w, h, type_, quality)
+        assert n == len(want) == oracle.record_size(type_, w, h)
+        assert np.array_equal(out[:n], want)
+    # error behaviour: 0, never a crash (converter.h:83)
+    out = np.zeros(8192, np.uint8)
+    pal, idx = tiles[0, :1024].copy(), tiles[0, 1024:].copy()
+    assert host.tcbh_convert_tile(type_, quality, p(pal), p(idx), 0, 5, p(out), 8192) == 0
+    assert host.tcbh_convert_tile(7, quality, p(pal), p(idx), 4, 4, p(out), 8192) == 0
+
+
+# ---- batch queue behind the TileThreadPool interface ----------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("slab,n", ((4096, 300), (64, 300), (7, 50)))
+def test_batch_queue_ordered_results(host, oracle, slab, n):
+    tiles = synth.mixed_tiles(n, 92)
+    stride = oracle.record_size(1)
+    out = np.zeros((n, stride), np.uint8); sizes = np.zeros(n, np.int32)
+    rc = host.tcbh_queue_encode(1, 9, 0, p(tiles), None, n, p(out), stride, p(sizes), slab, 0, 2)
+    assert rc == 0, host.tcbh_last_error()
+    assert (sizes == stride).all()
+    from tileconv_b200 import Encoder
+    with Encoder(1, 9) as enc:
+        assert np.array_equal(out, enc.encode(tiles))
+    assert np.array_equal(out[:16], oracle.encode_tiles(tiles[:16], 1, 9, threads=8))
+
+
+@pytest.mark.gpu
+def test_batch_queue_ragged_and_deflated(host, oracle):
+    tiles, wh = synth.ragged_tiles(40, 93)
+    stride = 8192
+    out = np.zeros((40, stride), np.uint8); sizes = np.zeros(40, np.int32)
+    rc = host.tcbh_queue_encode(3, 5, 1, p(tiles), p(wh), 40, p(out), stride, p(sizes), 16, 0, 3)
+    assert rc == 0, host.tcbh_last_error()
+    for i in range(40):
+        w, h = int(wh[i, 0]), int(wh[i, 1])
+        raw = zlib.decompress(out[i, :sizes[i]].tobytes())
+        assert raw == oracle.encode_tile(tiles[i, :1024], tiles[i, 1024:1024 + w * h], w, h, 3, 5).tobytes()
+        # same zlib parameters as the reference (deflateInit level 9, one shot): identical bytes
+        assert out[i, :sizes[i]].tobytes() == zlib.compress(raw, 9)
+
+
+@pytest.mark.gpu
+def test_batch_queue_reports_bad_tiles(host):
+    tiles = synth.mixed_tiles(3, 94)
+    wh = np.array([[64, 64], [0, 64], [64, 64]], np.uint16)
+    out = np.zeros((3, 2052), np.uint8); sizes = np.zeros(3, np.int32)
+    rc = host.tcbh_queue_encode(1, 2, 0, p(tiles), p(wh), 3, p(out), 2052, p(sizes), 2, 0, 1)
+    assert rc == 1 and sizes.tolist() == [2052, 0, 2052]
+
+
+# ---- container drivers ----------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("header", (True, False))
+@pytest.mark.parametrize("deflate", (0, 1))
+def test_tis_to_tbc_file(host, oracle, tmp_path, header, deflate):
+    tiles = synth.mixed_tiles(40, 95)
+    src, dst = str(tmp_path / "a.tis"), str(tmp_path / "a.tbc")
+    write_tis(src, tiles, header)
+    assert host.tcbh_encode_file(src.encode(), dst.encode(), 1, 9, deflate, 0 if header else 1, 2) == 0, host.tcbh_last_error()
+    code = 1 | (0 if deflate else 0x100)
+    want = expected_stream(oracle, b"TBC V1.0" + struct.pack("<II", code, 40), tiles, None, 1, 9, deflate)
+    assert open(dst, "rb").read() == want
+
+
+@pytest.mark.gpu
+def test_ka8_framing_1024_tiles(host, tmp_path):
+    """KA8: -T -u -t 1 on 1024 tiles -> 16 + 1024*(4+4+2048) bytes with the stated prefix."""
+    tiles = synth.mixed_tiles(1024, 96)
+    src, dst = str(tmp_path / "k.tis"), str(tmp_path / "k.tbc")
+    write_tis(src, tiles, header=False)
+    assert host.tcbh_encode_file(src.encode(), dst.encode(), 1, 2, 0, 1, 2) == 0
+    blob = open(dst, "rb").read()
+    assert len(blob) == 2105360
+    assert blob[:16] == bytes.fromhex("54424320 56312E30 01010000 00040000".replace(" ", ""))
+    assert blob[16:24] == bytes.fromhex("0408000040004000")
+    # headerless input without -T is refused and leaves no output behind
+    os.remove(dst)
+    assert host.tcbh_encode_file(src.encode(), dst.encode(), 1, 2, 0, 0, 2) != 0
+    assert not os.path.exists(dst)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("compressed", (False, True))
+def test_mos_to_mbc_file_with_edge_tiles(host, oracle, tmp_path, compressed):
+    mos, packed, wh = make_mos(150, 70, 97, compressed)        # 3x2 tiles, right/bottom edges partial
+    src, dst = str(tmp_path / "m.mos"), str(tmp_path / "m.mbc")
+    open(src, "wb").write(mos)
+    assert host.tcbh_encode_file(src.encode(), dst.encode(), 2, 9, 0, 0, 2) == 0, host.tcbh_last_error()
+    want = expected_stream(oracle, b"MBC V1.0" + struct.pack("<III", 2 | 0x100, 150, 70), packed, wh, 2, 9, 0)
+    assert open(dst, "rb").read() == want
+
+
+# ---- whole programs: the reference CLI vs the same CLI with the plugin dropped in -----------------
+@pytest.mark.gpu
+@pytest.mark.skipif(not (os.path.exists(REF_CLI) and os.path.exists(CUDA_CLI)), reason="oracle/_ref CLIs not built")
+@pytest.mark.parametrize("args", (["-T", "-u", "-t", "1", "-q", "-9"], ["-T", "-t", "3", "-q", "-7"], ["-u", "-t", "2", "-q", "-2"]))
+def test_reference_cli_with_plugin_writes_identical_files(tmp_path, args):
+    if "-T" in args:
+        src = str(tmp_path / "in.tis")
+        write_tis(src, np.concatenate([synth.mixed_tiles(70, 98), synth.keyed_tiles(30, 99)]), header=False)
+        ext = "tbc"
+    else:
+        src = str(tmp_path / "in.mos")
+        open(src, "wb").write(make_mos(200, 130, 100)[0])
+        ext = "mbc"
+    outs = []
+    for exe, name in ((REF_CLI, "ref"), (CUDA_CLI, "cuda")):
+        dst = str(tmp_path / f"{name}.{ext}")
+        res = subprocess.run([exe, "-s", "-j", "4", "-o", dst] + args + [src], capture_output=True, text=True, timeout=600)
+        assert res.returncode == 0 and os.path.exists(dst), res.stdout + res.stderr
+        outs.append(open(dst, "rb").read())
+    assert outs[0] == outs[1]
+    # and this repo's own driver agrees with both
+    dst = str(tmp_path / f"own.{ext}")
+    res = subprocess.run([TBC_ENCODE, "-s", "-o", dst] + args + [src], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr
+    assert open(dst, "rb").read() == outs[0]

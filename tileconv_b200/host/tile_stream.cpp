@@ -1,0 +1,208 @@
+#include "tile_stream.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <vector>
+
+#include <zlib.h>
+
+namespace tc {
+
+namespace {
+
+uint32_t rd32(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+uint32_t rd16(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
+void wr32(uint8_t* p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24); }
+
+bool readAll(const std::string& path, std::vector<uint8_t>& data)
+{
+  std::ifstream f(path, std::ios::binary | std::ios::ate);
+  if (!f) return false;
+  const std::streamoff size = f.tellg();
+  if (size < 0) return false;
+  data.resize((size_t)size);
+  f.seekg(0);
+  return size == 0 || (bool)f.read(reinterpret_cast<char*>(data.data()), size);
+}
+
+struct TileSource
+{
+  const uint8_t* palette;
+  const uint8_t* indices;
+  int width, height;
+};
+
+// Pushes `count` tiles through a pool created by createThreadPool() and writes
+// "u32 size + payload" per tile strictly in index order, exactly the protocol of
+// graphics.cpp:94-147: add one, drain whatever is next in order, after the last tile wait.
+template <class Provider>
+bool pumpTiles(const Options& options, unsigned count, Provider provider, std::FILE* out, std::string& error)
+{
+  ThreadPoolPtr pool = createThreadPool(options.getThreads(), 64);
+  const unsigned code = Options::GetEncodingCode(options.getEncoding(), options.isDeflate());
+  unsigned added = 0, written = 0;
+  while (added < count || !pool->finished()) {
+    if (added < count) {
+      const TileSource src = provider(added);
+      BytePtr indexed(new uint8_t[MAX_TILE_SIZE_8], std::default_delete<uint8_t[]>());
+      BytePtr palette(new uint8_t[PALETTE_SIZE], std::default_delete<uint8_t[]>());
+      BytePtr deflated(new uint8_t[MAX_TILE_SIZE_32 * 2], std::default_delete<uint8_t[]>());
+      std::memcpy(palette.get(), src.palette, PALETTE_SIZE);
+      std::memcpy(indexed.get(), src.indices, (size_t)src.width * src.height);
+      TileDataPtr tile(new TileData(options));
+      tile->setEncoding(true);
+      tile->setIndex((int)added);
+      tile->setType(code);
+      tile->setPaletteData(palette);
+      tile->setIndexedData(indexed);
+      tile->setDeflatedData(deflated);
+      tile->setWidth(src.width);
+      tile->setHeight(src.height);
+      pool->addTileData(tile);
+      ++added;
+    }
+    while (pool->hasResult() && pool->peekResult() != nullptr && (unsigned)pool->peekResult()->getIndex() == written) {
+      TileDataPtr done = pool->getResult();
+      if (done == nullptr || done->isError() || done->getSize() <= 0) {
+        error = (done != nullptr && !done->getErrorMsg().empty()) ? done->getErrorMsg() : "Error while encoding tile data";
+        return false;
+      }
+      uint8_t size[4];
+      wr32(size, (uint32_t)done->getSize());
+      if (std::fwrite(size, 1, 4, out) != 4 ||
+          std::fwrite(done->getDeflatedData().get(), 1, (size_t)done->getSize(), out) != (size_t)done->getSize()) {
+        error = "Error while writing tile data";
+        return false;
+      }
+      ++written;
+    }
+    if (added >= count) pool->waitForResult();
+  }
+  if (written < count) { error = "Missing tiles"; return false; }
+  return true;
+}
+
+struct OutputFile
+{
+  std::string path;
+  std::FILE* f;
+  bool keep = false;
+  explicit OutputFile(const std::string& p) : path(p), f(std::fopen(p.c_str(), "wb")) {}
+  ~OutputFile() { if (f) std::fclose(f); if (!keep) std::remove(path.c_str()); }
+};
+
+}  // namespace
+
+InputKind sniffInput(const std::string& path, bool assumeTis) noexcept
+{
+  std::ifstream f(path, std::ios::binary | std::ios::ate);
+  if (!f) return InputKind::UNKNOWN;
+  const std::streamoff size = f.tellg();
+  char sig[4] = { 0, 0, 0, 0 };
+  f.seekg(0);
+  f.read(sig, 4);
+  if (std::memcmp(sig, "TIS ", 4) == 0) return InputKind::TIS;
+  if (std::memcmp(sig, "MOS ", 4) == 0 || std::memcmp(sig, "MOSC", 4) == 0) return InputKind::MOS;
+  if (assumeTis && size > 0 && size % 5120 == 0) return InputKind::TIS;      // options.cpp:389-395
+  return InputKind::UNKNOWN;
+}
+
+bool encodeTisFile(const Options& options, const std::string& inFile, const std::string& outFile, std::string& error) noexcept
+{
+  std::vector<uint8_t> data;
+  if (inFile.empty() || outFile.empty() || inFile == outFile || !readAll(inFile, data)) { error = "Error opening input file"; return false; }
+  size_t first = 0;
+  uint32_t count = 0;
+  if (data.size() >= 4 && std::memcmp(data.data(), "TIS ", 4) == 0) {
+    // 'TIS ' 'V1  ' u32 count, u32 tile size (0x1400), u32 header size (>= 0x18), u32 dimension (0x40)
+    if (data.size() < 24) { error = "Invalid TIS header"; return false; }
+    if (std::memcmp(data.data() + 4, "V1  ", 4) != 0 && std::memcmp(data.data() + 4, "V2  ", 4) != 0) { error = "Invalid TIS version"; return false; }
+    count = rd32(data.data() + 8);
+    if (count == 0) { error = "No tiles found"; return false; }
+    if (rd32(data.data() + 12) != 0x1400) { error = "Invalid tile size"; return false; }
+    if (rd32(data.data() + 16) < 0x18) { error = "Invalid header size"; return false; }
+    if (rd32(data.data() + 20) != 0x40) { error = "Invalid tile dimensions"; return false; }
+    first = 24;                                            // the reference keeps reading right after these fields
+  } else if (options.assumeTis()) {
+    if (data.empty() || data.size() % 5120 != 0) { error = "Headerless TIS has wrong file size"; return false; }
+    count = (uint32_t)(data.size() / 5120);
+  } else {
+    error = "Invalid TIS signature";
+    return false;
+  }
+  if (data.size() < first + (size_t)count * 5120) { error = "Incomplete TIS file"; return false; }
+
+  OutputFile out(outFile);
+  if (!out.f) { error = "Error opening output file"; return false; }
+  uint8_t header[HEADER_TBC_SIZE];
+  std::memcpy(header, "TBC V1.0", 8);
+  wr32(header + 8, Options::GetEncodingCode(options.getEncoding(), options.isDeflate()));
+  wr32(header + 12, count);
+  if (std::fwrite(header, 1, sizeof(header), out.f) != sizeof(header)) { error = "Error while writing header"; return false; }
+  const uint8_t* base = data.data() + first;
+  auto provider = [&](unsigned i) { TileSource s = { base + (size_t)i * 5120, base + (size_t)i * 5120 + 1024, 64, 64 }; return s; };
+  if (!pumpTiles(options, count, provider, out.f, error)) return false;
+  out.keep = true;
+  return true;
+}
+
+bool encodeMosFile(const Options& options, const std::string& inFile, const std::string& outFile, std::string& error) noexcept
+{
+  std::vector<uint8_t> file, mos;
+  if (inFile.empty() || outFile.empty() || inFile == outFile || !readAll(inFile, file)) { error = "Error opening input file"; return false; }
+  if (file.size() >= 12 && std::memcmp(file.data(), "MOSC", 4) == 0) {
+    // 'MOSC' 'V1  ' u32 uncompressed size, zlib stream (graphics.cpp:861-891)
+    if (std::memcmp(file.data() + 4, "V1  ", 4) != 0) { error = "Invalid MOSC version"; return false; }
+    const uint32_t size = rd32(file.data() + 8);
+    if (size < 24) { error = "MOS size too small"; return false; }
+    mos.resize(size);
+    uLongf got = size;
+    if (uncompress(mos.data(), &got, file.data() + 12, (uLong)(file.size() - 12)) != Z_OK || got != size) {
+      error = "Error while decompressing MOSC input file";
+      return false;
+    }
+  } else {
+    mos.swap(file);
+  }
+  // 'MOS ' 'V1  ' u16 width, u16 height, u16 columns, u16 rows, u32 block size (0x40), u32 palette offset
+  if (mos.size() < 24 || std::memcmp(mos.data(), "MOS ", 4) != 0) { error = "Invalid MOS signature"; return false; }
+  if (std::memcmp(mos.data() + 4, "V1  ", 4) != 0) { error = "Unsupported MOS version"; return false; }
+  const unsigned width = rd16(mos.data() + 8), height = rd16(mos.data() + 10);
+  if (width == 0 || height == 0) { error = "Invalid MOS dimensions"; return false; }
+  if (rd16(mos.data() + 12) == 0 || rd16(mos.data() + 14) == 0) { error = "Invalid number of tiles"; return false; }
+  if (rd32(mos.data() + 16) != 0x40) { error = "Invalid tile dimensions"; return false; }
+  const uint32_t palOfs = rd32(mos.data() + 20);
+  if (palOfs < 24) { error = "MOS header too small"; return false; }
+  const unsigned cols = (width + 63) >> 6, rows = (height + 63) >> 6, count = cols * rows;
+  const size_t tableOfs = (size_t)palOfs + (size_t)count * PALETTE_SIZE, dataOfs = tableOfs + (size_t)count * 4;
+  if (mos.size() < dataOfs + (size_t)width * height) { error = "Incomplete or corrupted MOS file"; return false; }
+
+  OutputFile out(outFile);
+  if (!out.f) { error = "Error opening output file"; return false; }
+  uint8_t header[HEADER_MBC_SIZE];
+  std::memcpy(header, "MBC V1.0", 8);
+  wr32(header + 8, Options::GetEncodingCode(options.getEncoding(), options.isDeflate()));
+  wr32(header + 12, width);
+  wr32(header + 16, height);
+  if (std::fwrite(header, 1, sizeof(header), out.f) != sizeof(header)) { error = "Error while writing header"; return false; }
+  bool bad = false;
+  auto provider = [&](unsigned i) {
+    const unsigned row = i / cols, col = i % cols;
+    TileSource s;
+    s.width = (int)std::min(64u, width - col * 64);
+    s.height = (int)std::min(64u, height - row * 64);
+    s.palette = mos.data() + palOfs + (size_t)i * PALETTE_SIZE;
+    const size_t ofs = dataOfs + rd32(mos.data() + tableOfs + (size_t)i * 4);
+    if (ofs + (size_t)s.width * s.height > mos.size()) { bad = true; s.indices = mos.data() + dataOfs; }
+    else s.indices = mos.data() + ofs;
+    return s;
+  };
+  if (!pumpTiles(options, count, provider, out.f, error)) return false;
+  if (bad) { error = "Tile data outside of the MOS file"; return false; }
+  out.keep = true;
+  return true;
+}
+
+}  // namespace tc
