@@ -114,6 +114,11 @@ float tcb200_time_kernel_ms(tcb200_ctx* ctx, const void* d_tiles, const void* d_
  * second counting one per FMUL/FADD/FFMA instruction lane (so FLOP/s = 2x for fused). */
 double tcb200_fp32_peak(tcb200_ctx* ctx, int fused);
 
+/* Device self-test of the kernels' inlined reciprocal (MUFU.RCP + one Newton step, used for the 2x2
+ * least-squares denominators): compares it with IEEE 1.0f/x for every binary32 value of magnitude
+ * 2^-44 .. 2^10, both signs, and +0.  Returns the number of mismatches (0 = bit-exact), negative on error. */
+long long tcb200_selftest_reciprocal(tcb200_ctx* ctx);
+
 /* Kernels launched by this context so far (bench.py's gpu_launches). */
 long long tcb200_launch_count(const tcb200_ctx* ctx);
 

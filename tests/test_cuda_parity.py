@@ -136,6 +136,13 @@ def test_edge_cases(oracle):
             enc.encode(np.zeros((1, 5120), np.uint8), np.array([[65, 1]], np.uint16))
 
 
+def test_inlined_reciprocal_is_ieee_exact():
+    """The cluster solve replaces `1.0f/x` by MUFU.RCP + one Newton step without the compiler's range
+    check; every binary32 value of the range the solve can produce must give the IEEE result."""
+    with encoder(1, 9) as enc:
+        assert enc.selftest_reciprocal() == 0
+
+
 def test_pal_to_argb_matches_oracle(oracle):
     tiles = np.concatenate([synth.uniform_tiles(3, 61), synth.keyed_tiles(3, 62)])
     with encoder(1, 2) as enc:

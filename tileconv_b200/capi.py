@@ -40,6 +40,7 @@ SYMBOLS = [
     ("tcb200_pal_to_argb", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     ("tcb200_time_kernel_ms", ctypes.c_float, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]),
     ("tcb200_fp32_peak", ctypes.c_double, [ctypes.c_void_p, ctypes.c_int]),
+    ("tcb200_selftest_reciprocal", ctypes.c_longlong, [ctypes.c_void_p]),
     ("tcb200_launch_count", ctypes.c_longlong, [ctypes.c_void_p]),
 ]
 
@@ -180,6 +181,12 @@ class Encoder:
         v = float(self._lib.tcb200_fp32_peak(self._ctx, 1 if fused else 0))
         if v < 0:
             self._check(int(v), "tcb200_fp32_peak")
+        return v
+
+    def selftest_reciprocal(self) -> int:
+        v = int(self._lib.tcb200_selftest_reciprocal(self._ctx))
+        if v < 0:
+            self._check(v, "tcb200_selftest_reciprocal")
         return v
 
     def launch_count(self) -> int:

@@ -183,6 +183,21 @@ __global__ void __launch_bounds__(256) fp32_probe_kernel(float* out, int iters, 
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// Exhaustive check of reciprocal_exact() against the compiler's IEEE division over every binary32
+// value with bit pattern in [firstBits, lastBits], both signs, plus +0.
+__global__ void __launch_bounds__(256) reciprocal_selftest_kernel(unsigned firstBits, unsigned lastBits, unsigned long long* mismatches)
+{
+  unsigned long long bad = 0;
+  const unsigned long long span = (unsigned long long)lastBits - firstBits + 1ull;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < span; i += (unsigned long long)gridDim.x * blockDim.x) {
+    const float x = __uint_as_float(firstBits + (unsigned)i);
+    if (__float_as_uint(reciprocal_exact(x)) != __float_as_uint(1.0f / x)) ++bad;
+    if (__float_as_uint(reciprocal_exact(-x)) != __float_as_uint(1.0f / -x)) ++bad;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && __float_as_uint(reciprocal_exact(0.0f)) != 0x7f800000u) ++bad;
+  if (bad) atomicAdd(mismatches, bad);
+}
+
 // ================================================================================================
 // host: read-only tables
 // ================================================================================================
@@ -577,6 +592,24 @@ float tcb200_time_kernel_ms(tcb200_ctx* ctx, const void* d_tiles, const void* d_
   float ms = 0.0f;
   if (cudaEventElapsedTime(&ms, ctx->t0, ctx->t1) != cudaSuccess) return (float)TCB200_E_CUDA;
   return ms / (float)reps;
+}
+
+long long tcb200_selftest_reciprocal(tcb200_ctx* ctx)
+{
+  if (!ctx) return (long long)TCB200_E_ARG;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return (long long)TCB200_E_CUDA;
+  unsigned long long* dBad = nullptr;
+  if (cudaMalloc(&dBad, sizeof(unsigned long long)) != cudaSuccess) return (long long)TCB200_E_NOMEM;
+  cudaMemset(dBad, 0, sizeof(unsigned long long));
+  // 2^-44 (0x29800000) .. just below 2^10 (0x447fffff): well around the [1e-12, 256] the solve produces
+  reciprocal_selftest_kernel<<<ctx->sms * 8, 256, 0, ctx->stream[0]>>>(0x29800000u, 0x447fffffu, dBad);
+  ctx->launches.fetch_add(1);
+  unsigned long long bad = 0;
+  cudaError_t e = cudaStreamSynchronize(ctx->stream[0]);
+  if (e == cudaSuccess) e = cudaMemcpy(&bad, dBad, sizeof(bad), cudaMemcpyDeviceToHost);
+  cudaFree(dBad);
+  if (e != cudaSuccess) { fail(ctx, TCB200_E_CUDA, "tcb200_selftest_reciprocal", e); return (long long)TCB200_E_CUDA; }
+  return (long long)bad;
 }
 
 double tcb200_fp32_peak(tcb200_ctx* ctx, int fused)
