@@ -54,7 +54,7 @@ encode_tiles_kernel(const uint8_t* __restrict__ tiles, const uint16_t* __restric
 
     const int bw = (w + 3) >> 2, bh = (h + 3) >> 2, nblocks = bw * bh;
     const bool keyed = T.palette[0] == 0x0000ff00u;          // colors.cpp:47
-    if (tid == 0) T.out[0] = (uint32_t)w | ((uint32_t)h << 16);
+    if (tid == 0) { T.out[0] = (uint32_t)w | ((uint32_t)h << 16); T.nextJob = 0; }
 
     // ---- phase A: thread <-> block --------------------------------------------------------------
     uint8_t pending = 0xff;
@@ -88,24 +88,32 @@ encode_tiles_kernel(const uint8_t* __restrict__ tiles, const uint16_t* __restric
       }
     }
     jobs.count[lane] = pending;
-    __syncwarp();
 
     // ---- phase B: warp <-> block ----------------------------------------------------------------
+    // Blocks differ ~100x in work (points, orderings), so the tile's pending blocks are handed out
+    // dynamically: whichever warp is free takes the next one (shared-memory ticket counter).
     if (MODE != kRange) {
+      __syncthreads();
       WarpScratch& sc = allScratch[warp];
       constexpr int iterations = (MODE == kIterative) ? kMaxIterations : 1;
 #pragma unroll 1
-      for (int slot = 0; slot < 32; ++slot) {
-        const int n = jobs.count[slot];
+      for (;;) {
+        int ticket = 0;
+        if (lane == 0) ticket = atomicAdd(&T.nextJob, 1);
+        ticket = __shfl_sync(kFull, ticket, 0);
+        if (ticket >= nblocks) break;
+        const WarpJobs& jb = allJobs[ticket >> 5];
+        const int slot = ticket & 31;
+        const int n = jb.count[slot];
         if (n == 0xff) continue;
         float x = 0.0f, y = 0.0f, z = 0.0f, wgt = 0.0f;
         if (lane < n) {
-          const uint32_t k = jobs.key[lane][slot];
+          const uint32_t k = jb.key[lane][slot];
           x = T.unit[k & 255u]; y = T.unit[(k >> 8) & 255u]; z = T.unit[(k >> 16) & 255u];
-          wgt = jobs.weight[lane][slot];
+          wgt = jb.weight[lane][slot];
         }
-        const float principle[3] = { jobs.axis[0][slot], jobs.axis[1][slot], jobs.axis[2][slot] };
-        const uint32_t remapLo = jobs.remapLo[slot], remapHi = jobs.remapHi[slot], disabled = jobs.disabled[slot];
+        const float principle[3] = { jb.axis[0][slot], jb.axis[1][slot], jb.axis[2][slot] };
+        const uint32_t remapLo = jb.remapLo[slot], remapHi = jb.remapHi[slot], disabled = jb.disabled[slot];
         FitResult best;
         best.err = FLT_MAX; best.block = make_uint2(0u, 0u);
         if (TYPE == 1) {
@@ -116,7 +124,7 @@ encode_tiles_kernel(const uint8_t* __restrict__ tiles, const uint16_t* __restric
           cluster_fit<4>(sc, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, best);
         }
         if (lane == 0) {
-          uint32_t* dstColour = T.out + 1 + kWords * (warp * 32 + slot) + (TYPE == 1 ? 0 : 2);
+          uint32_t* dstColour = T.out + 1 + kWords * ticket + (TYPE == 1 ? 0 : 2);
           dstColour[0] = best.block.x; dstColour[1] = best.block.y;
         }
       }
