@@ -25,14 +25,15 @@ template <int TYPE> struct BlockWords { static constexpr int value = (TYPE == 1)
 
 // One CTA = one tile.  See bc_device.cuh for the phase structure.
 template <int TYPE, bool WEIGHT_ALPHA, int MODE>
-__global__ void __launch_bounds__(kThreads, (MODE == kRange) ? 4 : 3)
+__global__ void __launch_bounds__(kThreads, 4)
 encode_tiles_kernel(const uint8_t* __restrict__ tiles, const uint16_t* __restrict__ wh, int ntiles,
                     uint8_t* __restrict__ out, int outStride)
 {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  TileShared& T = *reinterpret_cast<TileShared*>(smem_raw);
-  WarpJobs* allJobs = reinterpret_cast<WarpJobs*>(smem_raw + sizeof(TileShared));
-  WarpScratch* allScratch = reinterpret_cast<WarpScratch*>(smem_raw + sizeof(TileShared) + sizeof(WarpJobs) * kWarps);
+  typedef TileShared<TYPE> Tile;
+  Tile& T = *reinterpret_cast<Tile*>(smem_raw);
+  WarpJobs* allJobs = reinterpret_cast<WarpJobs*>(smem_raw + sizeof(Tile));
+  WarpScratch* allScratch = reinterpret_cast<WarpScratch*>(smem_raw + sizeof(Tile) + sizeof(WarpJobs) * kWarps);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   WarpJobs& jobs = allJobs[warp];
@@ -75,15 +76,15 @@ encode_tiles_kernel(const uint8_t* __restrict__ tiles, const uint16_t* __restric
         dstColour[0] = c.x; dstColour[1] = c.y;
       } else if (MODE == kRange || s.count == 0) {
         float axis[3] = { 0.0f, 0.0f, 0.0f };
-        if (s.count > 0) principal_axis(T, jobs, lane, s.count, axis);
+        if (s.count > 0) principal_axis<WEIGHT_ALPHA>(T, jobs, lane, s.count, s.transparent, axis);
         uint2 c = range_fit_block<TYPE>(T, jobs, lane, s, axis);
         dstColour[0] = c.x; dstColour[1] = c.y;
       } else {
         float axis[3];
-        principal_axis(T, jobs, lane, s.count, axis);
+        principal_axis<WEIGHT_ALPHA>(T, jobs, lane, s.count, s.transparent, axis);
         jobs.axis[0][lane] = axis[0]; jobs.axis[1][lane] = axis[1]; jobs.axis[2][lane] = axis[2];
         jobs.remapLo[lane] = s.remapLo; jobs.remapHi[lane] = s.remapHi;
-        jobs.disabled[lane] = (uint16_t)s.disabled;
+        jobs.mask[lane] = (uint16_t)(TYPE == 1 ? s.disabled : s.transparent);
         pending = (uint8_t)s.count;
       }
     }
@@ -106,14 +107,15 @@ encode_tiles_kernel(const uint8_t* __restrict__ tiles, const uint16_t* __restric
         const int slot = ticket & 31;
         const int n = jb.count[slot];
         if (n == 0xff) continue;
+        const uint32_t mask = jb.mask[slot];
         float x = 0.0f, y = 0.0f, z = 0.0f, wgt = 0.0f;
         if (lane < n) {
           const uint32_t k = jb.key[lane][slot];
           x = T.unit[k & 255u]; y = T.unit[(k >> 8) & 255u]; z = T.unit[(k >> 16) & 255u];
-          wgt = jb.weight[lane][slot];
+          wgt = point_weight<WEIGHT_ALPHA>(k, mask);
         }
         const float principle[3] = { jb.axis[0][slot], jb.axis[1][slot], jb.axis[2][slot] };
-        const uint32_t remapLo = jb.remapLo[slot], remapHi = jb.remapHi[slot], disabled = jb.disabled[slot];
+        const uint32_t remapLo = jb.remapLo[slot], remapHi = jb.remapHi[slot], disabled = (TYPE == 1) ? mask : 0u;
         FitResult best;
         best.err = FLT_MAX; best.block = make_uint2(0u, 0u);
         if (TYPE == 1) {
@@ -407,7 +409,8 @@ tcb200_ctx* tcb200_create(int device, int type, int quality, int max_batch_tiles
   if (!tablesOk) { fail(nullptr, TCB200_E_ARG, "internal: candidate table overflow"); tcb200_destroy(ctx); return nullptr; }
   if ((e = cudaMemcpyToSymbol(g_tables, &hostTables, sizeof(hostTables))) != cudaSuccess) return bail("cudaMemcpyToSymbol(g_tables)", e);
 
-  ctx->smemBytes = sizeof(TileShared) + sizeof(WarpJobs) * kWarps + (ctx->mode == kRange ? 0 : sizeof(WarpScratch) * kWarps);
+  const size_t tileBytes = (type == 1) ? sizeof(TileShared<1>) : sizeof(TileShared<2>);
+  ctx->smemBytes = tileBytes + sizeof(WarpJobs) * kWarps + (ctx->mode == kRange ? 0 : sizeof(WarpScratch) * kWarps);
   KernelFn fn = select_kernel(ctx->type, ctx->weightAlpha, ctx->mode);
   if ((e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smemBytes)) != cudaSuccess)
     return bail("cudaFuncSetAttribute(MaxDynamicSharedMemorySize)", e);
