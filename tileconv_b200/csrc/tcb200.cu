@@ -119,11 +119,22 @@ encode_tiles_kernel(const uint8_t* __restrict__ tiles, const uint16_t* __restric
         FitResult best;
         best.err = FLT_MAX; best.block = make_uint2(0u, 0u);
         if (TYPE == 1) {
-          cluster_fit<3>(sc, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, best);
-          if (disabled == 0u)
-            cluster_fit<4>(sc, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, best);
+          if (disabled == 0u) {
+            // Compress3 then Compress4 both start from the principal-axis ordering: build it once and
+            // take the 4-colour sweep of iteration 0 while its prefix table is in place.
+            construct_ordering(sc, lane, n, x, y, z, wgt, principle[0], principle[1], principle[2], 0);
+            EarlySweep early;
+            const uint32_t* cand4 = g_tables.cand + g_tables.off4[n];
+            early.r = run_sweep<4>(sc, lane, n, cand4, g_tables.cnt4[n]);
+            early.entry = 0u;
+            if (early.r.c != kNoCandidate) early.entry = sweep_endpoints<4>(sc, n, cand4, early.r.c, early.win);
+            cluster_fit<3>(sc, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, true, nullptr, best);
+            cluster_fit<4>(sc, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, true, &early, best);
+          } else {
+            cluster_fit<3>(sc, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, false, nullptr, best);
+          }
         } else {
-          cluster_fit<4>(sc, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, best);
+          cluster_fit<4>(sc, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, false, nullptr, best);
         }
         if (lane == 0) {
           uint32_t* dstColour = T.out + 1 + kWords * ticket + (TYPE == 1 ? 0 : 2);
