@@ -11,6 +11,12 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # the shared libraries are build artefacts (git-ignored); build them if this checkout has none
+    needed = [os.path.join(ROOT, "tileconv_b200", "libtcb200.so"), os.path.join(ROOT, "tileconv_b200", "libtcb200_host.so"),
+              os.path.join(ROOT, "oracle", "libtco.so")]
+    if not all(os.path.exists(p) for p in needed):
+        import __graft_entry__
+        __graft_entry__.build()
 
 
 def _has_cuda() -> bool:

@@ -15,7 +15,7 @@ def main():
             with Encoder(t, q) as enc:
                 for name, tiles in sets.items():
                     t0 = time.time(); got = enc.encode(tiles); dt = time.time() - t0
-                    want = pyoracle.encode_tiles(tiles, t, q, threads=8)
+                    want = pyoracle.encode_tiles(tiles, t, q, threads=16)
                     bs = 8 if t == 1 else 16
                     g = got[:, 4:].reshape(n, 256, bs); w_ = want[:, 4:].reshape(n, 256, bs)
                     diff = (g != w_).any(axis=2).sum()
