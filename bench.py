@@ -334,6 +334,15 @@ def main() -> int:
     except Exception:
         pass
 
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            t = json.load(f).get(f"bc{args.type}_q{args.quality}_batch{B}")
+        if t:
+            traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
+    except Exception:
+        pass
+
     line = {
         "metric": f"tiles_per_s_bc{args.type}_q{args.quality}", "value": value, "unit": "tiles/s",
         "mpix_per_s": value * 4096 / 1e6,
@@ -349,7 +358,9 @@ def main() -> int:
         "wall_ms_per_step": 1e3 * t_wall / args.steps,
         "clocks": clocks,
         "roofline": {"bound": "fp32_alu", "achieved": achieved_tflops, "peak": peak_fused / 1e12, "unit": "TFLOP/s",
-                     "frac": achieved_tflops / (peak_fused / 1e12), "traffic": None,
+                     "frac": achieved_tflops / (peak_fused / 1e12), "traffic": traffic,
+                     "traffic_note": "DRAM bytes of one launch from the ncu capture in profiles/r1_traffic.json; algorithmic bytes per launch = "
+                                     + str(bytes_tile * B),
                      "peak_source": "FFMA loop measured live by tcb200_fp32_peak (an FFMA = 2 flops)",
                      "peak_unfused": peak_unfused / 1e12,
                      "frac_of_unfused": achieved_tflops / (peak_unfused / 1e12),

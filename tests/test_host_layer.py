@@ -112,6 +112,32 @@ def test_batch_queue_ordered_results(host, oracle, slab, n):
 
 
 @pytest.mark.gpu
+def test_batch_queue_shards_slabs_over_all_gpus(host, oracle):
+    """Multi-GPU path of the queue: consecutive slabs go to consecutive devices (tile-range sharding at
+    slab granularity, no collective); the ordered result stream must not depend on the device count."""
+    from tileconv_b200 import capi
+    gpus = capi.device_count()
+    if gpus < 2:
+        pytest.skip("needs at least 2 GPUs")
+    n = 700
+    tiles = synth.mixed_tiles(n, 191)
+    stride = oracle.record_size(3)
+    outs = []
+    for use in (1, gpus):
+        out = np.zeros((n, stride), np.uint8); sizes = np.zeros(n, np.int32)
+        rc = host.tcbh_queue_encode(3, 9, 0, p(tiles), None, n, p(out), stride, p(sizes), 48, use, 2)
+        assert rc == 0, host.tcbh_last_error()
+        outs.append(out)
+    assert np.array_equal(outs[0], outs[1])
+    assert np.array_equal(outs[1][:8], oracle.encode_tiles(tiles[:8], 3, 9, threads=8))
+    # and the C ABI on every device gives the same records
+    from tileconv_b200 import Encoder
+    for d in range(gpus):
+        with Encoder(3, 9, device=d) as enc:
+            assert np.array_equal(enc.encode(tiles[:64]), outs[0][:64])
+
+
+@pytest.mark.gpu
 def test_batch_queue_ragged_and_deflated(host, oracle):
     tiles, wh = synth.ragged_tiles(40, 93)
     stride = 8192
