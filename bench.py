@@ -157,6 +157,27 @@ def cpu_reference_rate(pool: np.ndarray, sample: int, type_: int, quality: int, 
     return len(tiles) / best, cores, ("reference" if use_ref else "port"), per_tile
 
 
+def as_shipped_cli_rate(pool: np.ndarray, sample: int, type_: int, quality: int):
+    """BASELINE.md baseline A: the reference CLI as shipped (its own polling thread pool), wall clock of
+    `tileconv -s -T -u -t T -q -Q -j 0` on a headerless TIS of `sample` tiles.  None when the CLI was not
+    built (oracle/_ref/tileconv_ref needs /root/reference at build time)."""
+    import tempfile
+    exe = os.path.join(ROOT, "oracle", "_ref", "tileconv_ref")
+    if not os.path.exists(exe):
+        return None
+    with tempfile.TemporaryDirectory() as tmp:
+        src, dst = os.path.join(tmp, "in.tis"), os.path.join(tmp, "out.tbc")
+        pool[:sample].tofile(src)
+        t0 = time.perf_counter()
+        res = subprocess.run([exe, "-s", "-T", "-u", "-t", str(type_), "-q", f"-{quality}", "-j", "0", "-o", dst, src],
+                             capture_output=True, text=True)
+        dt = time.perf_counter() - t0
+        if res.returncode != 0 or not os.path.exists(dst):
+            return None
+    return {"value": sample / dt, "unit": "tiles/s", "sample": f"{sample} tiles through the reference CLI (-j 0, -u), wall clock incl. file I/O",
+            "note": "capped by the reference pool's 64-tile window and 50 ms polling sleeps (SURVEY.md F4)"}
+
+
 def flops_per_tile(per_tile: dict) -> float:
     """W = C3*138 + C4*160 + F_fixed, F_fixed(n) ~ 30 n + 8*27 per cluster block."""
     return (per_tile["cand3"] * F3_OPS + per_tile["cand4"] * F4_OPS
@@ -319,6 +340,7 @@ def main() -> int:
     from oracle import pyoracle
     sample = min(args.cpu_sample, POOL_TILES)
     cpu_rate, cores, kind, per_tile = cpu_reference_rate(pool, sample, args.type, args.quality)
+    shipped = as_shipped_cli_rate(pool, min(sample, 1024), args.type, args.quality)
     # parity of the measured outputs: the first `sample` tiles of the batch are pool tiles (copy 0)
     want = pyoracle.encode_tiles(pool[:256], args.type, args.quality, threads=cores)
     parity_ok = bool(np.array_equal(dev_result[:256], want)) if rank * B == 0 else None
@@ -370,7 +392,8 @@ def main() -> int:
                      "hbm": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
                              "bytes_per_tile": bytes_tile, "peak_source": f"MEASURED_PEAKS.json ({hbm_src})"}},
         "cpu_baseline": {"value": cpu_rate, "unit": "tiles/s", "cores": cores, "kind": kind,
-                         "sample": f"{sample} pool tiles, {cores} threads over the reference's TileData::encode (-u), restated squish"},
+                         "sample": f"{sample} pool tiles, {cores} threads over the reference's TileData::encode (-u), restated squish",
+                         "as_shipped_cli": shipped},
         "parity_spot_check": parity_ok,
         "modes": modes,
     }

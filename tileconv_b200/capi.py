@@ -50,7 +50,8 @@ class TcbError(RuntimeError):
 
 
 def library_path() -> str:
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libtcb200.so")
+    # TCB200_LIB selects an alternative build of the same library (kernel tuning sweeps)
+    return os.environ.get("TCB200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libtcb200.so")
 
 
 def load_library() -> ctypes.CDLL:
