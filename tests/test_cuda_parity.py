@@ -136,6 +136,36 @@ def test_edge_cases(oracle):
             enc.encode(np.zeros((1, 5120), np.uint8), np.array([[65, 1]], np.uint16))
 
 
+def nan_axis_tile():
+    """Blocks whose principal axis is NaN: two opaque pixels (255,0,0) and (0,255,0), everything else
+    keyed transparent.  Their covariance is [[.5,-.5,0],[-.5,.5,0],[0,0,0]], the power iteration starts
+    from (1,1,1), gets the zero vector and divides by its maximum: 0 * (1/0) = NaN (App. A.4).  The
+    reference then sorts NaN projections, i.e. leaves the order alone; the CUDA path has a dedicated
+    branch for non-finite projections."""
+    t = np.zeros((1, 5120), np.uint8)
+    t[0, 0:4] = synth.KEY_ENTRY
+    t[0, 4:8] = [0, 0, 255, 0]        # index 1: red   (B,G,R,x)
+    t[0, 8:12] = [0, 255, 0, 0]       # index 2: green
+    t[0, 12:16] = [255, 0, 0, 0]      # index 3: blue
+    idx = t[0, 1024:].reshape(64, 64)
+    rng = np.random.default_rng(5)
+    for by in range(16):
+        for bx in range(16):
+            cells = rng.permutation(16)[:2]
+            pair = [(1, 2), (2, 1), (1, 3), (3, 2)][(by * 16 + bx) % 4]
+            for c, v in zip(cells, pair):
+                idx[4 * by + c // 4, 4 * bx + c % 4] = v
+    return t
+
+
+@pytest.mark.parametrize("type_,quality", ((1, 4), (1, 9), (3, 9), (2, 6)))
+def test_nan_principal_axis_blocks(oracle, type_, quality):
+    t = nan_axis_tile()
+    with encoder(type_, quality) as enc:
+        got = enc.encode(t)
+    assert_blocks_equal(got, oracle.encode_tiles(t, type_, quality), type_, "NaN-axis blocks")
+
+
 def test_inlined_reciprocal_is_ieee_exact():
     """The cluster solve replaces `1.0f/x` by MUFU.RCP + one Newton step without the compiler's range
     check; every binary32 value of the range the solve can produce must give the IEEE result."""

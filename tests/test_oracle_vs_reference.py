@@ -32,3 +32,12 @@ def test_ragged_tiles(ref, type_):
             a = ref.encode_tile(tiles[i, :1024], tiles[i, 1024:1024 + w * h], w, h, type_, q)
             b = ref.ref_encode_tile(tiles[i, :1024], tiles[i, 1024:1024 + w * h], w, h, type_, q)
             assert np.array_equal(a, b), (i, w, h, q)
+
+
+def test_nan_axis_blocks(ref):
+    """Degenerate covariance (NaN principal axis): the restated path must still follow the reference glue."""
+    from test_cuda_parity import nan_axis_tile
+    t = nan_axis_tile()
+    for type_ in (1, 2, 3):
+        for q in (4, 9):
+            assert np.array_equal(ref.encode_tiles(t, type_, q), ref.ref_encode_tiles(t, type_, q, threads=1))
