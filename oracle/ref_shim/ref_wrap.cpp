@@ -36,6 +36,7 @@ void addTotals()
 tc::Encoding encodingOf(int type)
 {
   switch (type) {
+    case 0: return tc::Encoding::RAW;
     case 1: return tc::Encoding::BC1;
     case 2: return tc::Encoding::BC2;
     case 3: return tc::Encoding::BC3;

@@ -75,6 +75,33 @@ def expected_stream(oracle, header, tiles, wh, type_, quality, deflate):
     return out
 
 
+# ---- type 0 (raw passthrough) and the queue's host lane: no GPU involved ---------------------------
+def test_raw_passthrough_through_queue_and_plugin(host, oracle):
+    """"-t 0": the tile record is u16 w, u16 h, palette, indices (converter_raw.cpp:48-62).  These tiles
+    never touch the GPU: the queue runs the tile's own functor on host workers, like the reference pool."""
+    tiles, wh = synth.ragged_tiles(20, 90)
+    stride = 4 + 1024 + 4096
+    out = np.zeros((20, stride * 2), np.uint8); sizes = np.zeros(20, np.int32)
+    assert host.tcbh_queue_encode(0, 9, 0, p(tiles), p(wh), 20, p(out), stride * 2, p(sizes), 8, 0, 3) == 0
+    ref = oracle.reference()
+    for i in range(20):
+        w, h = int(wh[i, 0]), int(wh[i, 1])
+        want = bytes([w, 0, h, 0]) + tiles[i, :1024 + w * h].tobytes()
+        assert sizes[i] == len(want) and out[i, :sizes[i]].tobytes() == want
+        one = np.zeros(stride, np.uint8)
+        pal, idx = tiles[i, :1024].copy(), tiles[i, 1024:].copy()
+        assert host.tcbh_convert_tile(0, 9, p(pal), p(idx), w, h, p(one), stride) == len(want)
+        assert one[:len(want)].tobytes() == want
+        if ref is not None:
+            assert oracle.ref_encode_tile(tiles[i, :1024], tiles[i, 1024:1024 + w * h], w, h, 0, 9).tobytes() == want
+    # deflated variant: zlib level 9, one shot (tiledata.cpp:139-148)
+    assert host.tcbh_queue_encode(0, 9, 1, p(tiles), p(wh), 20, p(out), stride * 2, p(sizes), 8, 0, 2) == 0
+    for i in range(20):
+        w, h = int(wh[i, 0]), int(wh[i, 1])
+        want = bytes([w, 0, h, 0]) + tiles[i, :1024 + w * h].tobytes()
+        assert out[i, :sizes[i]].tobytes() == zlib.compress(want, 9)
+
+
 # ---- per-tile plugin surface --------------------------------------------------------------------
 @pytest.mark.gpu
 @pytest.mark.parametrize("type_,quality", ((1, 9), (2, 2), (3, 7)))
@@ -206,7 +233,8 @@ def test_mos_to_mbc_file_with_edge_tiles(host, oracle, tmp_path, compressed):
 # ---- whole programs: the reference CLI vs the same CLI with the plugin dropped in -----------------
 @pytest.mark.gpu
 @pytest.mark.skipif(not (os.path.exists(REF_CLI) and os.path.exists(CUDA_CLI)), reason="oracle/_ref CLIs not built")
-@pytest.mark.parametrize("args", (["-T", "-u", "-t", "1", "-q", "-9"], ["-T", "-t", "3", "-q", "-7"], ["-u", "-t", "2", "-q", "-2"]))
+@pytest.mark.parametrize("args", (["-T", "-u", "-t", "1", "-q", "-9"], ["-T", "-t", "3", "-q", "-7"], ["-u", "-t", "2", "-q", "-2"],
+                                  ["-T", "-t", "0"], ["-u", "-t", "0"]))
 def test_reference_cli_with_plugin_writes_identical_files(tmp_path, args):
     if "-T" in args:
         src = str(tmp_path / "in.tis")

@@ -10,7 +10,7 @@ using namespace tc;
 
 namespace {
 
-Encoding encodingOf(int type) { return type == 1 ? Encoding::BC1 : type == 2 ? Encoding::BC2 : type == 3 ? Encoding::BC3 : Encoding::UNKNOWN; }
+Encoding encodingOf(int type) { return type == 0 ? Encoding::RAW : type == 1 ? Encoding::BC1 : type == 2 ? Encoding::BC2 : type == 3 ? Encoding::BC3 : Encoding::UNKNOWN; }
 thread_local std::string t_error;
 
 }  // namespace

@@ -18,8 +18,8 @@ int main(int argc, char** argv)
     auto next = [&]() -> const char* { return (i + 1 < argc) ? argv[++i] : ""; };
     if (a == "-t") {
       const int t = std::atoi(next());
-      if (t < 1 || t > 3) { std::fprintf(stderr, "Unsupported pixel encoding type\n"); return 1; }
-      options.setEncoding(t == 1 ? tc::Encoding::BC1 : t == 2 ? tc::Encoding::BC2 : tc::Encoding::BC3);
+      if (t < 0 || t > 3) { std::fprintf(stderr, "Unsupported pixel encoding type\n"); return 1; }
+      options.setEncoding(t == 0 ? tc::Encoding::RAW : t == 1 ? tc::Encoding::BC1 : t == 2 ? tc::Encoding::BC2 : tc::Encoding::BC3);
     } else if (a == "-q") {
       const char* q = next();                      // "<decode><encode>", '-' keeps the default (options.cpp:129-152)
       if (std::strlen(q) >= 2 && q[1] >= '0' && q[1] <= '9') options.setEncodingQuality(q[1] - '0');
@@ -31,7 +31,7 @@ int main(int argc, char** argv)
     else input = a;
   }
   if (input.empty()) {
-    std::fprintf(stderr, "usage: tbc_encode [-t 1|2|3] [-q -N] [-u] [-T] [-j n] [-s] [-o out] in.tis|in.mos\n");
+    std::fprintf(stderr, "usage: tbc_encode [-t 0|1|2|3] [-q -N] [-u] [-T] [-j n] [-s] [-o out] in.tis|in.mos\n");
     return 1;
   }
   const tc::InputKind kind = tc::sniffInput(input, options.assumeTis());

@@ -6,6 +6,8 @@
 #include <cstring>
 #include <thread>
 
+#include <zlib.h>
+
 namespace tc {
 
 int Options::getThreads() const noexcept
@@ -37,8 +39,18 @@ TileData& TileData::operator()() noexcept
   std::unique_ptr<uint8_t[]> encoded(new uint8_t[(size_t)space + HEADER_TILE_ENCODED_SIZE]);
   const int written = converter->convert(m_palette.get(), m_indexed.get(), encoded.get(), m_width, m_height);
   if (written <= 0) { m_errorMsg = "Error while encoding tile data\n"; return *this; }
-  std::memcpy(m_deflated.get(), encoded.get(), (size_t)written);
-  m_size = written;
+  if (m_options.isDeflate()) {
+    // one-shot zlib stream at level 9 into a buffer of twice the size (tiledata.cpp:139-148, compress.cpp:36)
+    uLongf dstLen = (uLongf)written * 2;
+    if (compress2(m_deflated.get(), &dstLen, encoded.get(), (uLong)written, 9) != Z_OK) {
+      m_errorMsg = "Error while compressing tile data\n";
+      return *this;
+    }
+    m_size = (int)dstLen;
+  } else {
+    std::memcpy(m_deflated.get(), encoded.get(), (size_t)written);
+    m_size = written;
+  }
   m_error = false;
   return *this;
 }

@@ -54,6 +54,57 @@ TileBatchQueue::~TileBatchQueue() noexcept
 {
   while (!m_inflight.empty()) harvestOldest();
   for (Gpu& g : m_gpus) tcb200_destroy(g.ctx);
+  {
+    std::lock_guard<std::mutex> lock(m_hostMutex);
+    m_hostStop = true;
+  }
+  m_hostWake.notify_all();
+  for (std::thread& t : m_workers) t.join();
+}
+
+// ---- host lane: tiles the GPU path does not cover run their own functor on worker threads ----------
+void TileBatchQueue::hostWorker() noexcept
+{
+  for (;;) {
+    TileDataPtr tile;
+    {
+      std::unique_lock<std::mutex> lock(m_hostMutex);
+      m_hostWake.wait(lock, [this] { return m_hostStop || !m_hostQueue.empty(); });
+      if (m_hostQueue.empty()) return;          // stop requested and nothing left
+      tile = m_hostQueue.front();
+      m_hostQueue.pop_front();
+      ++m_hostActive;
+    }
+    (*tile)();                                   // TileData::operator(): encode() or decode() on the CPU
+    {
+      std::lock_guard<std::mutex> lock(m_hostMutex);
+      m_hostDone.push_back(tile);
+      --m_hostActive;
+    }
+    m_hostDoneCv.notify_all();
+  }
+}
+
+void TileBatchQueue::runOnHost(TileDataPtr tile) noexcept
+{
+  if (m_workers.empty())
+    for (unsigned t = 0; t < m_threads; ++t) m_workers.emplace_back(&TileBatchQueue::hostWorker, this);
+  {
+    // bounded like the reference's input queue (getMaxTiles(), tilethreadpool_posix.cpp:66)
+    std::unique_lock<std::mutex> lock(m_hostMutex);
+    m_hostDoneCv.wait(lock, [this] { return m_hostQueue.size() < (size_t)std::max(1u, getMaxTiles()); });
+    m_hostQueue.push_back(tile);
+  }
+  m_hostWake.notify_one();
+}
+
+void TileBatchQueue::drainHostResults() noexcept
+{
+  std::lock_guard<std::mutex> lock(m_hostMutex);
+  while (!m_hostDone.empty()) {
+    getResultQueue().push(m_hostDone.front());
+    m_hostDone.pop_front();
+  }
 }
 
 bool TileBatchQueue::ensureContexts(const Options& options) noexcept
@@ -99,12 +150,17 @@ void TileBatchQueue::failTile(TileDataPtr tile) noexcept
 void TileBatchQueue::addTileData(TileDataPtr tileData) noexcept
 {
   if (tileData == nullptr) return;
+  poll();
+  {
+    const Encoding enc = tileData->getOptions().getEncoding();
+    const bool gpuTile = tileData->isEncoding() && (enc == Encoding::BC1 || enc == Encoding::BC2 || enc == Encoding::BC3);
+    if (!gpuTile) { runOnHost(tileData); return; }
+  }
   const int w = tileData->getWidth(), h = tileData->getHeight();
   const bool valid = tileData->isEncoding() && tileData->getPaletteData() != nullptr && tileData->getIndexedData() != nullptr &&
                      tileData->getDeflatedData() != nullptr && tileData->getIndex() >= 0 && w > 0 && h > 0 && w <= 64 && h <= 64;
   if (!valid || !ensureContexts(tileData->getOptions())) { failTile(tileData); return; }
 
-  poll();
   Slot* slot = &m_slots[m_current];
   // the slot being filled may still be in flight from the previous lap: wait for it (this is the
   // only place the producer blocks, the analogue of "queue full" in tilethreadpool_posix.cpp:66)
@@ -179,6 +235,7 @@ void TileBatchQueue::harvestOldest() noexcept
 
 void TileBatchQueue::poll() noexcept
 {
+  drainHostResults();
   while (!m_inflight.empty()) {
     Slot& slot = m_slots[m_inflight.front()];
     if (tcb200_slab_ready(m_gpus[(size_t)slot.gpu].ctx, slot.slab) != 1) break;
@@ -206,14 +263,24 @@ void TileBatchQueue::waitForResult() noexcept
   // the caller has nothing more to add right now: ship the partly filled slab, then block until
   // something is ready or the queue is idle
   submitCurrent();
-  if (getResultQueue().empty()) harvestOldest();
+  drainHostResults();
+  if (!getResultQueue().empty()) return;
+  if (!m_inflight.empty()) { harvestOldest(); return; }
+  std::unique_lock<std::mutex> lock(m_hostMutex);
+  m_hostDoneCv.wait(lock, [this] { return !m_hostDone.empty() || (m_hostQueue.empty() && m_hostActive == 0); });
+  while (!m_hostDone.empty()) { getResultQueue().push(m_hostDone.front()); m_hostDone.pop_front(); }
 }
 
 bool TileBatchQueue::finished() noexcept
 {
   poll();
   const bool filling = !m_slots.empty() && !m_slots[m_current].tiles.empty();
-  return !filling && m_inflight.empty() && getResultQueue().empty();
+  bool hostIdle;
+  {
+    std::lock_guard<std::mutex> lock(m_hostMutex);
+    hostIdle = m_hostQueue.empty() && m_hostActive == 0 && m_hostDone.empty();
+  }
+  return !filling && m_inflight.empty() && hostIdle && getResultQueue().empty();
 }
 
 // ---- the two link-time factory functions of tilethreadpool_base.h:38,44 --------------------------

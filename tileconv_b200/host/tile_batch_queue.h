@@ -12,13 +12,22 @@
 // come back through the base class's index-ordered result heap, so callers that drain with
 // peekResult()->getIndex() == next (graphics.cpp:125-143) work unchanged.
 //
+// Tiles that are not a BC1/BC2/BC3 ENCODE -- the decode direction (tbcToTIS / mbcToMOS feed the same
+// pool, graphics.cpp:172-275,395-517) and the raw passthrough type 0 -- are outside the GPU path: they
+// run the tile's own functor (TileData::operator(), tiledata.cpp:58-66) on `threadNum` host worker
+// threads, exactly what the reference's pool does with every tile, so the queue stays a complete
+// replacement for createThreadPool()'s object.
+//
 // zlib framing (TileData::encode's deflate step, tiledata.cpp:139-148) stays on the host: when
 // Options::isDeflate() is set the harvested records are deflated (level 9, compress.cpp:36) by
 // `threadNum` host threads before they are published.
 #ifndef TCB200_TILE_BATCH_QUEUE_H
 #define TCB200_TILE_BATCH_QUEUE_H
 
+#include <condition_variable>
 #include <deque>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include "tc_iface.h"
@@ -59,6 +68,9 @@ private:
   void harvestOldest() noexcept;     // blocking
   void poll() noexcept;              // non-blocking: publish every slab that has completed, in order
   void failTile(TileDataPtr tile) noexcept;
+  void runOnHost(TileDataPtr tile) noexcept;   // non-GPU tiles: the reference's per-tile functor on a worker
+  void hostWorker() noexcept;
+  void drainHostResults() noexcept;            // main thread: move finished host tiles into the result heap
 
   unsigned m_threads;
   int m_slabTiles, m_maxGpus;
@@ -69,6 +81,13 @@ private:
   size_t m_current = 0;              // slot being filled
   std::deque<size_t> m_inflight;     // submitted slots, oldest first
   std::string m_error;
+  // host side lane (decode / raw tiles)
+  std::vector<std::thread> m_workers;
+  std::mutex m_hostMutex;
+  std::condition_variable m_hostWake, m_hostDoneCv;
+  std::deque<TileDataPtr> m_hostQueue, m_hostDone;
+  int m_hostActive = 0;
+  bool m_hostStop = false;
 };
 
 }  // namespace tc
