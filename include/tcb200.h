@@ -103,6 +103,15 @@ void  tcb200_host_free(void* p);
  * expand stage; the encode kernels expand in shared memory and never write pixels to HBM. */
 int tcb200_pal_to_argb(tcb200_ctx* ctx, const uint8_t* tiles, int n, uint8_t* bgra);
 
+/* Decode direction, front half only ("next" row N3): n encoded tile records (stride =
+ * tcb200_record_stride, each starting with its own u16 w, u16 h) -> n x 16384 bytes of pixels in
+ * memory order B,G,R,A at row pitch w (the first w*h*4 bytes of each 16 KiB slot), i.e. what
+ * ConverterDxt::decodeTile + decodeBlockDxt1/3/5 produce (tileconv/converter_dxt.cpp:147-176,251-430).
+ * reference_bc3_alpha != 0 reproduces the reference's BC3 alpha decode, which reads its endpoints and
+ * index bits from bytes 2..9 of the block (converter_dxt.cpp:351-359); 0 follows the BC3 format.
+ * Quantising the pixels back to a palette (Colors::ARGBToPal, libimagequant) stays on the host. */
+int tcb200_decode(tcb200_ctx* ctx, const uint8_t* records, int n, uint8_t* bgra, int reference_bc3_alpha);
+
 /* Kernel-only timing aid for bench.py: runs the encode kernel `reps` times on device-resident data
  * on the context's compute stream and returns the mean milliseconds per launch measured with CUDA
  * events on that stream (negative error code on failure). */

@@ -123,12 +123,27 @@ def pal_to_argb(indexed: np.ndarray, palette: np.ndarray) -> np.ndarray:
     return out
 
 
-def decode_tile(record: np.ndarray, type_: int) -> np.ndarray:
+def decode_tile(record: np.ndarray, type_: int, reference_quirk: bool = False) -> np.ndarray:
+    """(h, w, 4) pixels in memory order B,G,R,A.  reference_quirk mimics the reference's BC3 alpha decode."""
     record = np.ascontiguousarray(record, np.uint8)
     w = int(record[0]) | (int(record[1]) << 8); h = int(record[2]) | (int(record[3]) << 8)
     out = np.zeros((h, w, 4), np.uint8)
-    n = oracle().tco_decode_tile(_p(record), type_, _p(out))
+    fn = oracle().tco_decode_tile_ex
+    fn.restype = ctypes.c_int
+    n = fn(_p(record), type_, _p(out), 1 if reference_quirk else 0)
     assert n == w * h * 4
+    return out
+
+
+def ref_decode_tile(record: np.ndarray, type_: int) -> np.ndarray:
+    """The reference's own block decoders (oracle/_ref): (h, w, 4) pixels in memory order R,G,B,A."""
+    lib = reference()
+    record = np.ascontiguousarray(record, np.uint8)
+    w = int(record[0]) | (int(record[1]) << 8); h = int(record[2]) | (int(record[3]) << 8)
+    out = np.zeros((h, w, 4), np.uint8)
+    lib.tcref_decode_tile.restype = ctypes.c_int
+    n = lib.tcref_decode_tile(_p(record), int(record.size), type_, _p(out), int(out.size))
+    assert n == w * h * 4, n
     return out
 
 

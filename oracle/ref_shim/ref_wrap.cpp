@@ -14,8 +14,12 @@
 #include <vector>
 #include <squish.h>
 #include "converter.h"
+#include "converterfactory.h"
 #include "options.h"
 #include "tiledata.h"
+
+extern thread_local std::vector<unsigned char> g_tcref_captured_pixels;   /* ref_stubs.cpp */
+extern thread_local int g_tcref_captured_w, g_tcref_captured_h;
 
 namespace {
 
@@ -121,6 +125,26 @@ int tcref_encode_tiles(const uint8_t* tiles, int n, int type, int quality, uint8
   int total = 0;
   for (int f : failed) total += f;
   return total;
+}
+
+/* The reference's block decoders on one encoded tile record (u16 w, u16 h, blocks): runs
+ * ConverterDxt::convert in the decode direction (converter_dxt.cpp:78-89); the quantiser stub captures
+ * the decoded pixels, returned here in memory order R,G,B,A.  Returns w*h*4 or 0. */
+int tcref_decode_tile(const uint8_t* encoded, int encodedSize, int type, uint8_t* rgba, int capacity)
+{
+  tc::Options options;
+  options.setVerbosity(0);
+  tc::ConverterPtr converter = tc::ConverterFactory::GetConverter(options, (unsigned)type);
+  if (converter == nullptr || !converter->canDecode() || encodedSize < 4) return 0;
+  converter->setEncoding(false);
+  converter->setColorFormat(tc::Converter::ColorFormat::ARGB);
+  std::vector<uint8_t> enc(encoded, encoded + encodedSize + 16), palette(1024), indexed(64 * 64);
+  g_tcref_captured_pixels.clear();
+  converter->convert(palette.data(), indexed.data(), enc.data());      /* fails in the stubbed quantiser, by design */
+  const int bytes = g_tcref_captured_w * g_tcref_captured_h * 4;
+  if (bytes <= 0 || bytes > capacity) return 0;
+  std::memcpy(rgba, g_tcref_captured_pixels.data(), (size_t)bytes);
+  return bytes;
 }
 
 void tcref_totals_reset(void) { std::lock_guard<std::mutex> lock(g_totalsMutex); std::memset(&g_totals, 0, sizeof(g_totals)); }

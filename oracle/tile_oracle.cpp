@@ -130,7 +130,12 @@ void decode_colour(const uint8_t* src, bool bc1, uint8_t out[64])
   }
 }
 
-void decode_block(const uint8_t* src, int type, uint8_t out[64])
+/* referenceQuirk: the reference's decodeBlockDxt5 takes its two alpha endpoints and the 48 index bits
+ * from src[2..9] instead of src[0..7] (converter_dxt.cpp:351-359 loads the control word at &src[2] and
+ * then peels alpha[0], alpha[1] off it).  That is a decode-side defect of the reference (out of scope
+ * here); the oracle decodes BC3 alpha per the format unless asked to mimic it, which the tests do when
+ * they compare with the reference's own decoder. */
+void decode_block(const uint8_t* src, int type, uint8_t out[64], bool referenceQuirk)
 {
   if (type == 1) { decode_colour(src, true, out); return; }
   decode_colour(src + 8, false, out);
@@ -140,7 +145,8 @@ void decode_block(const uint8_t* src, int type, uint8_t out[64])
       out[4 * i + 3] = (uint8_t)((alpha & 0x0f) | ((alpha & 0x0f) << 4));
   } else {
     uint8_t a[8];
-    a[0] = src[0]; a[1] = src[1];
+    const uint8_t* as = referenceQuirk ? src + 2 : src;
+    a[0] = as[0]; a[1] = as[1];
     if (a[0] > a[1]) {
       for (int k = 1; k < 7; ++k) a[1 + k] = (uint8_t)(((7 - k) * (unsigned)a[0] + k * (unsigned)a[1]) / 7);
     } else {
@@ -148,7 +154,7 @@ void decode_block(const uint8_t* src, int type, uint8_t out[64])
       a[6] = 0; a[7] = 255;
     }
     uint64_t ctrl = 0;
-    for (int k = 0; k < 6; ++k) ctrl |= (uint64_t)src[2 + k] << (8 * k);
+    for (int k = 0; k < 6; ++k) ctrl |= (uint64_t)as[2 + k] << (8 * k);
     for (int i = 0; i < 16; ++i, ctrl >>= 3) out[4 * i + 3] = a[ctrl & 7];
   }
 }
@@ -241,7 +247,10 @@ void tco_totals_get(SquishOracleCounters* out) { std::lock_guard<std::mutex> loc
 
 /* Decodes one encoded tile record (u16 w, u16 h, blocks) into w*h pixels, memory order B,G,R,A
  * (ColorFormat::ARGB as a little-endian u32).  Returns w*h*4 or 0. */
-int tco_decode_tile(const uint8_t* encoded, int type, uint8_t* bgra)
+int tco_decode_tile_ex(const uint8_t* encoded, int type, uint8_t* bgra, int referenceQuirk);
+int tco_decode_tile(const uint8_t* encoded, int type, uint8_t* bgra) { return tco_decode_tile_ex(encoded, type, bgra, 0); }
+
+int tco_decode_tile_ex(const uint8_t* encoded, int type, uint8_t* bgra, int referenceQuirk)
 {
   if (!encoded || !bgra || type < 1 || type > 3) return 0;
   const int w = encoded[0] | (encoded[1] << 8), h = encoded[2] | (encoded[3] << 8);
@@ -251,7 +260,7 @@ int tco_decode_tile(const uint8_t* encoded, int type, uint8_t* bgra)
   for (int y = 0; y < h; y += 4)
     for (int x = 0; x < w; x += 4) {
       uint8_t px[64];
-      decode_block(src, type, px);
+      decode_block(src, type, px, referenceQuirk != 0);
       src += blockSize;
       for (int py = 0; py < 4 && y + py < h; ++py)
         for (int qx = 0; qx < 4 && x + qx < w; ++qx)

@@ -219,3 +219,24 @@ def test_device_slab_and_sharded_paths_agree(oracle):
             parts.append(enc.encode(tiles[lo:hi]))
         assert np.array_equal(np.concatenate(parts), want)
         assert enc.launch_count() >= 8
+
+
+@pytest.mark.parametrize("type_", (1, 2, 3))
+def test_decode_matches_restated_reference_decoder(oracle, type_):
+    """Next-row N3: BCn decode on the GPU against the oracle's restatement of decodeBlockDxt1/3/5 (which
+    tests/test_oracle_vs_reference.py pins to the reference's own decoders), full and ragged tiles,
+    both BC3 alpha modes."""
+    tiles, wh = synth.ragged_tiles(12, 111)
+    full = np.concatenate([synth.keyed_tiles(3, 112), synth.uniform_tiles(2, 113)])
+    with encoder(type_, 4) as enc:
+        rec_r = enc.encode(tiles, wh)
+        rec_f = enc.encode(full)
+        for quirk in (False, True):
+            px_r = enc.decode(rec_r, quirk)
+            px_f = enc.decode(rec_f, quirk)
+            for i in range(len(tiles)):
+                w, h = int(wh[i, 0]), int(wh[i, 1])
+                want = oracle.decode_tile(rec_r[i], type_, quirk)
+                assert np.array_equal(px_r[i, :w * h].reshape(h, w, 4), want), (i, w, h, quirk)
+            for i in range(len(full)):
+                assert np.array_equal(px_f[i].reshape(64, 64, 4), oracle.decode_tile(rec_f[i], type_, quirk))

@@ -38,6 +38,7 @@ SYMBOLS = [
     ("tcb200_host_alloc", ctypes.c_void_p, [ctypes.c_size_t]),
     ("tcb200_host_free", None, [ctypes.c_void_p]),
     ("tcb200_pal_to_argb", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+    ("tcb200_decode", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]),
     ("tcb200_time_kernel_ms", ctypes.c_float, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]),
     ("tcb200_fp32_peak", ctypes.c_double, [ctypes.c_void_p, ctypes.c_int]),
     ("tcb200_selftest_reciprocal", ctypes.c_longlong, [ctypes.c_void_p]),
@@ -199,6 +200,15 @@ class Encoder:
         n = tiles.shape[0]
         out = np.zeros((n, 4096, 4), dtype=np.uint8)
         self._check(self._lib.tcb200_pal_to_argb(self._ctx, _ptr(tiles) if n else None, n, _ptr(out) if n else None), "tcb200_pal_to_argb")
+        return out
+
+    def decode(self, records: np.ndarray, reference_bc3_alpha: bool = False) -> np.ndarray:
+        """(n, stride) encoded records -> (n, 4096, 4) B,G,R,A pixels at row pitch w of each tile."""
+        records = np.ascontiguousarray(records, dtype=np.uint8).reshape(-1, self.stride)
+        n = records.shape[0]
+        out = np.zeros((n, 4096, 4), dtype=np.uint8)
+        self._check(self._lib.tcb200_decode(self._ctx, _ptr(records) if n else None, n, _ptr(out) if n else None,
+                                            1 if reference_bc3_alpha else 0), "tcb200_decode")
         return out
 
     # -- slabs ----------------------------------------------------------------------------------

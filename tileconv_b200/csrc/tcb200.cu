@@ -183,6 +183,90 @@ pal_to_argb_kernel(const uint8_t* __restrict__ tiles, int ntiles, uint32_t* __re
   }
 }
 
+// BC1/BC2/BC3 tile DECODE (next-row N3): the integer block decoders of the reference
+// (ConverterDxt::decodeTile + decodeBlockDxt1/3/5 + unpackColors565, tileconv/converter_dxt.cpp:147-176,
+// 251-430), one thread per 4x4 block, pixels written as B,G,R,A (ColorFormat::ARGB) at row pitch w.
+// refBc3Alpha mimics the reference's BC3 alpha decode, which reads its endpoints and index bits two
+// bytes late (converter_dxt.cpp:351-359); 0 decodes BC3 alpha per the format.
+template <int TYPE>
+__global__ void __launch_bounds__(kThreads)
+decode_tiles_kernel(const uint8_t* __restrict__ records, int ntiles, int stride, uint32_t* __restrict__ bgra, int refBc3Alpha)
+{
+  constexpr int kWords = BlockWords<TYPE>::value;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const uint32_t* rec = reinterpret_cast<const uint32_t*>(records + (size_t)tile * stride);
+    const uint32_t header = __ldg(rec);
+    const int w = (int)(header & 0xffffu), h = (int)(header >> 16);
+    if (w <= 0 || h <= 0 || w > 64 || h > 64) continue;
+    const int bw = (w + 3) >> 2, bh = (h + 3) >> 2;
+    const int b = threadIdx.x;
+    if (b >= bw * bh) continue;
+    uint32_t words[kWords];
+#pragma unroll
+    for (int k = 0; k < kWords; ++k) words[k] = __ldg(rec + 1 + kWords * b + k);
+    const uint32_t ends = words[kWords - 2], codes = words[kWords - 1];
+    const uint32_t c0 = ends & 0xffffu, c1 = ends >> 16;
+    // unpackColors565: 5/6/5 bits replicated into 8
+    uint32_t e0[3], e1[3];
+    e0[0] = ((c0 << 3) & 0xf8u) | ((c0 >> 2) & 0x07u); e0[1] = ((c0 >> 3) & 0xfcu) | ((c0 >> 9) & 0x03u); e0[2] = ((c0 >> 8) & 0xf8u) | ((c0 >> 13) & 0x07u);
+    e1[0] = ((c1 << 3) & 0xf8u) | ((c1 >> 2) & 0x07u); e1[1] = ((c1 >> 3) & 0xfcu) | ((c1 >> 9) & 0x03u); e1[2] = ((c1 >> 8) & 0xf8u) | ((c1 >> 13) & 0x07u);
+    const bool four = (TYPE != 1) || c0 > c1;
+    uint32_t pal[4];
+    pal[0] = e0[0] | (e0[1] << 8) | (e0[2] << 16) | 0xff000000u;
+    pal[1] = e1[0] | (e1[1] << 8) | (e1[2] << 16) | 0xff000000u;
+    if (four) {
+      pal[2] = ((2 * e0[0] + e1[0]) / 3) | (((2 * e0[1] + e1[1]) / 3) << 8) | (((2 * e0[2] + e1[2]) / 3) << 16) | 0xff000000u;
+      pal[3] = ((e0[0] + 2 * e1[0]) / 3) | (((e0[1] + 2 * e1[1]) / 3) << 8) | (((e0[2] + 2 * e1[2]) / 3) << 16) | 0xff000000u;
+    } else {
+      pal[2] = ((e0[0] + e1[0]) >> 1) | (((e0[1] + e1[1]) >> 1) << 8) | (((e0[2] + e1[2]) >> 1) << 16) | 0xff000000u;
+      pal[3] = 0u;
+    }
+    // alpha
+    uint32_t alpha[16];
+    if (TYPE == 2) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { uint32_t a = (words[i >> 3] >> (4 * (i & 7))) & 0xfu; alpha[i] = a | (a << 4); }
+    } else if (TYPE == 3) {
+      // bytes of the block as one 128-bit little-endian value
+      const uint64_t lo = (uint64_t)words[0] | ((uint64_t)words[1] << 32), hi = (uint64_t)words[2] | ((uint64_t)words[3] << 32);
+      const uint64_t v = refBc3Alpha ? ((lo >> 16) | (hi << 48)) : lo;       // start two bytes late in the quirk mode
+      const uint32_t a0 = (uint32_t)(v & 0xffu), a1 = (uint32_t)((v >> 8) & 0xffu);
+      uint32_t table[8];
+      table[0] = a0; table[1] = a1;
+      if (a0 > a1) {
+#pragma unroll
+        for (int k = 1; k < 7; ++k) table[1 + k] = ((7 - k) * a0 + k * a1) / 7;
+      } else {
+#pragma unroll
+        for (int k = 1; k < 5; ++k) table[1 + k] = ((5 - k) * a0 + k * a1) / 5;
+        table[6] = 0u; table[7] = 255u;
+      }
+      const uint64_t ctrl = v >> 16;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const uint32_t idx = (uint32_t)(ctrl >> (3 * i)) & 7u;
+        uint32_t a = table[0];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) a = (idx == (uint32_t)k) ? table[k] : a;
+        alpha[i] = a;
+      }
+    }
+    const int bx = b % bw, by = b / bw;
+    uint32_t* dst = bgra + (size_t)tile * 4096;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int x = 4 * bx + (i & 3), y = 4 * by + (i >> 2);
+      if (x < w && y < h) {
+        const uint32_t code = (codes >> (2 * i)) & 3u;
+        uint32_t px = pal[0];
+        px = code == 1u ? pal[1] : px; px = code == 2u ? pal[2] : px; px = code == 3u ? pal[3] : px;
+        if (TYPE != 1) px = (px & 0x00ffffffu) | (alpha[i] << 24);
+        dst[y * w + x] = px;
+      }
+    }
+  }
+}
+
 // FP32 pipe probe: 8 independent chains per thread, no memory traffic.
 template <bool FUSED>
 __global__ void __launch_bounds__(256) fp32_probe_kernel(float* out, int iters, float seed)
@@ -598,6 +682,34 @@ int tcb200_pal_to_argb(tcb200_ctx* ctx, const uint8_t* tiles, int n, uint8_t* bg
     if (e != cudaSuccess) { cudaFree(dPix); return fail(ctx, TCB200_E_CUDA, "tcb200_pal_to_argb", e); }
   }
   cudaFree(dPix);
+  return TCB200_OK;
+}
+
+int tcb200_decode(tcb200_ctx* ctx, const uint8_t* records, int n, uint8_t* bgra, int reference_bc3_alpha)
+{
+  if (!ctx) return TCB200_E_ARG;
+  if (n < 0 || (n > 0 && (!records || !bgra))) return fail(ctx, TCB200_E_ARG, "tcb200_decode: bad argument");
+  TCB_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream[0];
+  uint32_t* dPix = nullptr;
+  cudaError_t e = cudaSuccess;
+  for (int first = 0; first < n && e == cudaSuccess; first += ctx->capacity) {
+    const int m = (n - first < ctx->capacity) ? n - first : ctx->capacity;
+    if (!dPix) e = cudaMalloc(&dPix, (size_t)(n < ctx->capacity ? n : ctx->capacity) * 4096 * 4);
+    if (e == cudaSuccess) e = cudaMemsetAsync(dPix, 0, (size_t)m * 4096 * 4, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->dOut[0], records + (size_t)first * ctx->stride, (size_t)m * ctx->stride, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+      if (ctx->type == 1) decode_tiles_kernel<1><<<m, kThreads, 0, st>>>(ctx->dOut[0], m, ctx->stride, dPix, reference_bc3_alpha);
+      else if (ctx->type == 2) decode_tiles_kernel<2><<<m, kThreads, 0, st>>>(ctx->dOut[0], m, ctx->stride, dPix, reference_bc3_alpha);
+      else decode_tiles_kernel<3><<<m, kThreads, 0, st>>>(ctx->dOut[0], m, ctx->stride, dPix, reference_bc3_alpha);
+      ctx->launches.fetch_add(1);
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(bgra + (size_t)first * 4096 * 4, dPix, (size_t)m * 4096 * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  }
+  cudaFree(dPix);
+  if (e != cudaSuccess) return fail(ctx, TCB200_E_CUDA, "tcb200_decode", e);
   return TCB200_OK;
 }
 
