@@ -1,4 +1,7 @@
 // Plain-C test and tooling entry points into the C++ host layer (used by tests/ through ctypes).
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -50,7 +53,11 @@ int tcbh_queue_encode(int type, int quality, int deflate, const uint8_t* tiles, 
   options.setDeflate(deflate != 0);
   TileBatchQueue pool((unsigned)(threads > 0 ? threads : 1), 64, slabTiles > 0 ? slabTiles : 4096, gpus);
   int added = 0, drained = 0, problems = 0;
+  typedef std::chrono::steady_clock Clock;
+  double tMake = 0, tAdd = 0, tDrain = 0, tWait = 0;
+  const bool profile = std::getenv("TCBH_PROFILE") != nullptr;
   while (added < n || !pool.finished()) {
+    Clock::time_point t0 = Clock::now();
     if (added < n) {
       const int w = wh ? wh[2 * added] : 64, h = wh ? wh[2 * added + 1] : 64;
       BytePtr palette(new uint8_t[1024], std::default_delete<uint8_t[]>());
@@ -64,9 +71,13 @@ int tcbh_queue_encode(int type, int quality, int deflate, const uint8_t* tiles, 
       tile->setType(Options::GetEncodingCode(options.getEncoding(), options.isDeflate()));
       tile->setPaletteData(palette); tile->setIndexedData(indexed); tile->setDeflatedData(deflated);
       tile->setWidth(w); tile->setHeight(h);
+      Clock::time_point t1 = Clock::now();
       pool.addTileData(tile);
       ++added;
+      Clock::time_point t2 = Clock::now();
+      if (profile) { tMake += std::chrono::duration<double>(t1 - t0).count(); tAdd += std::chrono::duration<double>(t2 - t1).count(); }
     }
+    Clock::time_point t3 = Clock::now();
     while (pool.hasResult() && pool.peekResult() != nullptr && pool.peekResult()->getIndex() == drained) {
       TileDataPtr done = pool.getResult();
       sizes[drained] = done->getSize();
@@ -74,8 +85,11 @@ int tcbh_queue_encode(int type, int quality, int deflate, const uint8_t* tiles, 
       else std::memcpy(out + (size_t)drained * outStride, done->getDeflatedData().get(), (size_t)done->getSize());
       ++drained;
     }
+    Clock::time_point t4 = Clock::now();
     if (added >= n) pool.waitForResult();
+    if (profile) { tDrain += std::chrono::duration<double>(t4 - t3).count(); tWait += std::chrono::duration<double>(Clock::now() - t4).count(); }
   }
+  if (profile) std::fprintf(stderr, "tcbh_queue_encode n=%d: make %.1f ms, addTileData %.1f ms, drain %.1f ms, wait %.1f ms\n", n, tMake * 1e3, tAdd * 1e3, tDrain * 1e3, tWait * 1e3);
   t_error = pool.lastError();
   return problems + (n - drained);
 }

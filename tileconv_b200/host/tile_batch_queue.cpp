@@ -1,9 +1,9 @@
 #include "tile_batch_queue.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
-#include <thread>
 
 #include <zlib.h>
 
@@ -52,59 +52,35 @@ TileBatchQueue::TileBatchQueue(unsigned threadNum, unsigned tileNum, int slabTil
 
 TileBatchQueue::~TileBatchQueue() noexcept
 {
-  while (!m_inflight.empty()) harvestOldest();
-  for (Gpu& g : m_gpus) tcb200_destroy(g.ctx);
-  {
-    std::lock_guard<std::mutex> lock(m_hostMutex);
-    m_hostStop = true;
-  }
-  m_hostWake.notify_all();
+  { std::lock_guard<std::mutex> lock(m_inMutex); m_stop.store(true); }
+  m_inCv.notify_all(); m_inSpaceCv.notify_all();
+  { std::lock_guard<std::mutex> lock(m_flightMutex); }
+  m_flightCv.notify_all(); m_slotFreeCv.notify_all();
+  { std::lock_guard<std::mutex> lock(m_hostMutex); }
+  m_hostWake.notify_all(); m_hostSpaceCv.notify_all();
+  if (m_feeder.joinable()) m_feeder.join();
+  m_flightCv.notify_all();
+  if (m_harvester.joinable()) m_harvester.join();
   for (std::thread& t : m_workers) t.join();
+  for (Gpu& g : m_gpus) tcb200_destroy(g.ctx);
 }
 
-// ---- host lane: tiles the GPU path does not cover run their own functor on worker threads ----------
-void TileBatchQueue::hostWorker() noexcept
+void TileBatchQueue::setError(const std::string& msg) noexcept
 {
-  for (;;) {
-    TileDataPtr tile;
-    {
-      std::unique_lock<std::mutex> lock(m_hostMutex);
-      m_hostWake.wait(lock, [this] { return m_hostStop || !m_hostQueue.empty(); });
-      if (m_hostQueue.empty()) return;          // stop requested and nothing left
-      tile = m_hostQueue.front();
-      m_hostQueue.pop_front();
-      ++m_hostActive;
-    }
-    (*tile)();                                   // TileData::operator(): encode() or decode() on the CPU
-    {
-      std::lock_guard<std::mutex> lock(m_hostMutex);
-      m_hostDone.push_back(tile);
-      --m_hostActive;
-    }
-    m_hostDoneCv.notify_all();
-  }
+  std::lock_guard<std::mutex> lock(m_doneMutex);
+  m_error = msg;
 }
 
-void TileBatchQueue::runOnHost(TileDataPtr tile) noexcept
+std::string TileBatchQueue::lastError() noexcept
 {
-  if (m_workers.empty())
-    for (unsigned t = 0; t < m_threads; ++t) m_workers.emplace_back(&TileBatchQueue::hostWorker, this);
-  {
-    // bounded like the reference's input queue (getMaxTiles(), tilethreadpool_posix.cpp:66)
-    std::unique_lock<std::mutex> lock(m_hostMutex);
-    m_hostDoneCv.wait(lock, [this] { return m_hostQueue.size() < (size_t)std::max(1u, getMaxTiles()); });
-    m_hostQueue.push_back(tile);
-  }
-  m_hostWake.notify_one();
+  std::lock_guard<std::mutex> lock(m_doneMutex);
+  return m_error;
 }
 
-void TileBatchQueue::drainHostResults() noexcept
+int TileBatchQueue::getActiveThreads() noexcept
 {
-  std::lock_guard<std::mutex> lock(m_hostMutex);
-  while (!m_hostDone.empty()) {
-    getResultQueue().push(m_hostDone.front());
-    m_hostDone.pop_front();
-  }
+  std::lock_guard<std::mutex> lock(m_doneMutex);
+  return m_pending > 0 ? 1 : 0;
 }
 
 bool TileBatchQueue::ensureContexts(const Options& options) noexcept
@@ -116,13 +92,13 @@ bool TileBatchQueue::ensureContexts(const Options& options) noexcept
   int devices = tcb200_device_count();
   if (m_maxGpus > 0) devices = std::min(devices, m_maxGpus);
   if (devices <= 0 || m_type == 0) {
-    m_error = devices <= 0 ? "no CUDA device (there is no CPU fallback)" : "pixel type is not BC1/BC2/BC3";
+    setError(devices <= 0 ? "no CUDA device (there is no CPU fallback)" : "pixel type is not BC1/BC2/BC3");
     return false;
   }
   for (int d = 0; d < devices; ++d) {
     tcb200_ctx* ctx = tcb200_create(d, m_type, m_quality, m_slabTiles);
     if (ctx == nullptr) {
-      m_error = tcb200_last_error(nullptr);
+      setError(tcb200_last_error(nullptr));
       for (Gpu& g : m_gpus) tcb200_destroy(g.ctx);
       m_gpus.clear();
       return false;
@@ -134,67 +110,170 @@ bool TileBatchQueue::ensureContexts(const Options& options) noexcept
   for (int s = 0; s < slabs; ++s)
     for (int d = 0; d < devices; ++d) {
       Slot slot; slot.gpu = d; slot.slab = s;
+      slot.tiles.reserve((size_t)m_slabTiles);
       m_slots.push_back(slot);
     }
-  m_current = 0;
+  m_inLimit = (size_t)m_slabTiles * m_slots.size();
+  m_feeder = std::thread(&TileBatchQueue::feederMain, this);
+  m_harvester = std::thread(&TileBatchQueue::harvesterMain, this);
   return true;
 }
 
-void TileBatchQueue::failTile(TileDataPtr tile) noexcept
+// ---- hand-over to the caller ------------------------------------------------------------------------
+void TileBatchQueue::publish(std::vector<TileDataPtr>& tiles) noexcept
 {
-  // the reference reports a failed tile through size 0 (graphics.cpp:1140 refuses to write it)
-  tile->setSize(0);
-  getResultQueue().push(tile);
+  {
+    std::lock_guard<std::mutex> lock(m_doneMutex);
+    for (TileDataPtr& t : tiles) m_done.push_back(t);
+    m_pending -= (long long)tiles.size();
+  }
+  m_doneCv.notify_all();
 }
 
+void TileBatchQueue::drainDone() noexcept
+{
+  std::lock_guard<std::mutex> lock(m_doneMutex);
+  while (!m_done.empty()) {
+    getResultQueue().push(m_done.front());
+    m_done.pop_front();
+  }
+}
+
+// ---- caller's thread ----------------------------------------------------------------------------------
 void TileBatchQueue::addTileData(TileDataPtr tileData) noexcept
 {
   if (tileData == nullptr) return;
-  poll();
-  {
-    const Encoding enc = tileData->getOptions().getEncoding();
-    const bool gpuTile = tileData->isEncoding() && (enc == Encoding::BC1 || enc == Encoding::BC2 || enc == Encoding::BC3);
-    if (!gpuTile) { runOnHost(tileData); return; }
-  }
+  if ((++m_addsSincePoll & 255u) == 0u) drainDone();
+  const Encoding enc = tileData->getOptions().getEncoding();
+  const bool gpuTile = tileData->isEncoding() && (enc == Encoding::BC1 || enc == Encoding::BC2 || enc == Encoding::BC3);
+  if (!gpuTile) { runOnHost(tileData); return; }
+
   const int w = tileData->getWidth(), h = tileData->getHeight();
-  const bool valid = tileData->isEncoding() && tileData->getPaletteData() != nullptr && tileData->getIndexedData() != nullptr &&
+  const bool valid = tileData->getPaletteData() != nullptr && tileData->getIndexedData() != nullptr &&
                      tileData->getDeflatedData() != nullptr && tileData->getIndex() >= 0 && w > 0 && h > 0 && w <= 64 && h <= 64;
-  if (!valid || !ensureContexts(tileData->getOptions())) { failTile(tileData); return; }
-
-  Slot* slot = &m_slots[m_current];
-  // the slot being filled may still be in flight from the previous lap: wait for it (this is the
-  // only place the producer blocks, the analogue of "queue full" in tilethreadpool_posix.cpp:66)
-  while (std::find(m_inflight.begin(), m_inflight.end(), m_current) != m_inflight.end()) harvestOldest();
-
-  tcb200_ctx* ctx = m_gpus[(size_t)slot->gpu].ctx;
-  uint8_t* in = tcb200_slab_input(ctx, slot->slab);
-  uint16_t* sizes = tcb200_slab_sizes(ctx, slot->slab);
-  if (in == nullptr || sizes == nullptr) { m_error = tcb200_last_error(ctx); failTile(tileData); return; }
-  const size_t i = slot->tiles.size();
-  uint8_t* record = in + i * TCB200_TILE_RECORD;
-  std::memcpy(record, tileData->getPaletteData().get(), PALETTE_SIZE);
-  std::memcpy(record + PALETTE_SIZE, tileData->getIndexedData().get(), (size_t)w * h);
-  sizes[2 * i] = (uint16_t)w; sizes[2 * i + 1] = (uint16_t)h;
-  slot->tiles.push_back(tileData);
-  if ((int)slot->tiles.size() == m_slabTiles) submitCurrent();
+  if (!valid || !ensureContexts(tileData->getOptions())) {
+    // the reference reports a failed tile through size 0 (graphics.cpp:1140 refuses to write it)
+    tileData->setSize(0);
+    getResultQueue().push(tileData);
+    return;
+  }
+  { std::lock_guard<std::mutex> lock(m_doneMutex); ++m_pending; }
+  {
+    // "blocks execution as long as the input queue is full" (tilethreadpool_base.h:64)
+    std::unique_lock<std::mutex> lock(m_inMutex);
+    m_inSpaceCv.wait(lock, [this] { return m_inQueue.size() < m_inLimit || m_stop; });
+    m_inQueue.push_back(tileData);
+  }
+  m_inCv.notify_one();
 }
 
-void TileBatchQueue::submitCurrent() noexcept
+TileDataPtr TileBatchQueue::getResult() noexcept
 {
-  if (m_slots.empty()) return;
-  Slot& slot = m_slots[m_current];
+  // slabs are harvested in submission order, so anything not yet published has a larger index than
+  // the heap's top: the done list only needs a look when the heap is empty
+  if (getResultQueue().empty()) drainDone();
+  if (getResultQueue().empty()) return TileDataPtr();
+  TileDataPtr top = getResultQueue().top();
+  getResultQueue().pop();
+  return top;
+}
+
+const TileDataPtr TileBatchQueue::peekResult() noexcept
+{
+  if (getResultQueue().empty()) drainDone();
+  return getResultQueue().empty() ? TileDataPtr() : getResultQueue().top();
+}
+
+void TileBatchQueue::waitForResult() noexcept
+{
+  // the caller has nothing more to add right now: ship the partly filled slab, then block until
+  // something is ready or the queue is idle
+  { std::lock_guard<std::mutex> lock(m_inMutex); m_flush = true; }
+  m_inCv.notify_one();
+  drainDone();
+  if (!getResultQueue().empty()) return;
+  std::unique_lock<std::mutex> lock(m_doneMutex);
+  m_doneCv.wait(lock, [this] { return !m_done.empty() || m_pending == 0; });
+  while (!m_done.empty()) { getResultQueue().push(m_done.front()); m_done.pop_front(); }
+}
+
+bool TileBatchQueue::finished() noexcept
+{
+  drainDone();
+  std::lock_guard<std::mutex> lock(m_doneMutex);
+  return m_pending == 0 && m_done.empty() && getResultQueue().empty();
+}
+
+// ---- feeder: tiles -> pinned slabs -> GPU --------------------------------------------------------------
+void TileBatchQueue::submitSlot(size_t slotIndex) noexcept
+{
+  Slot& slot = m_slots[slotIndex];
   if (slot.tiles.empty()) return;
   tcb200_ctx* ctx = m_gpus[(size_t)slot.gpu].ctx;
+  { std::lock_guard<std::mutex> lock(m_flightMutex); slot.busy = true; }
   if (tcb200_slab_submit(ctx, slot.slab, (int)slot.tiles.size()) != TCB200_OK) {
-    m_error = tcb200_last_error(ctx);
-    harvest(slot, false);
-  } else {
-    m_inflight.push_back(m_current);
+    setError(tcb200_last_error(ctx));
+    finishSlot(slot, false);
+    { std::lock_guard<std::mutex> lock(m_flightMutex); slot.busy = false; }
+    return;
   }
-  m_current = (m_current + 1) % m_slots.size();
+  { std::lock_guard<std::mutex> lock(m_flightMutex); m_inflight.push_back(slotIndex); }
+  m_flightCv.notify_one();
 }
 
-void TileBatchQueue::harvest(Slot& slot, bool ok) noexcept
+void TileBatchQueue::feederMain() noexcept
+{
+  std::atomic<bool>& stop = m_stop;
+  size_t current = 0;
+  bool acquired = false;            // the feeder owns slot `current` (it is not in flight)
+  std::deque<TileDataPtr> batch;
+  for (;;) {
+    bool flush = false;
+    {
+      std::unique_lock<std::mutex> lock(m_inMutex);
+      m_inCv.wait(lock, [this] { return m_stop || m_flush || !m_inQueue.empty(); });
+      if (m_stop) return;
+      batch.swap(m_inQueue);
+      flush = m_flush;
+      m_flush = false;
+    }
+    m_inSpaceCv.notify_all();
+    for (TileDataPtr& tile : batch) {
+      Slot& slot = m_slots[current];
+      if (!acquired) {
+        // the slot may still be in flight from the previous lap (the analogue of "queue full");
+        // the harvester empties slot.tiles before it clears `busy`
+        std::unique_lock<std::mutex> lock(m_flightMutex);
+        m_slotFreeCv.wait(lock, [&] { return !slot.busy || stop.load(); });
+        if (stop.load()) return;
+        acquired = true;
+      }
+      tcb200_ctx* ctx = m_gpus[(size_t)slot.gpu].ctx;
+      uint8_t* in = tcb200_slab_input(ctx, slot.slab);
+      uint16_t* sizes = tcb200_slab_sizes(ctx, slot.slab);
+      if (in == nullptr || sizes == nullptr) {
+        setError(tcb200_last_error(ctx));
+        tile->setSize(0);
+        std::vector<TileDataPtr> one(1, tile);
+        publish(one);
+        continue;
+      }
+      const int w = tile->getWidth(), h = tile->getHeight();
+      const size_t i = slot.tiles.size();
+      uint8_t* record = in + i * TCB200_TILE_RECORD;
+      std::memcpy(record, tile->getPaletteData().get(), PALETTE_SIZE);
+      std::memcpy(record + PALETTE_SIZE, tile->getIndexedData().get(), (size_t)w * h);
+      sizes[2 * i] = (uint16_t)w; sizes[2 * i + 1] = (uint16_t)h;
+      slot.tiles.push_back(tile);
+      if ((int)slot.tiles.size() == m_slabTiles) { submitSlot(current); current = (current + 1) % m_slots.size(); acquired = false; }
+    }
+    batch.clear();
+    if (flush && acquired && !m_slots[current].tiles.empty()) { submitSlot(current); current = (current + 1) % m_slots.size(); acquired = false; }
+  }
+}
+
+// ---- harvester: GPU -> the tiles' own buffers ----------------------------------------------------------
+void TileBatchQueue::finishSlot(Slot& slot, bool ok) noexcept
 {
   tcb200_ctx* ctx = m_gpus[(size_t)slot.gpu].ctx;
   const uint8_t* out = ok ? tcb200_slab_output(ctx, slot.slab) : nullptr;
@@ -218,69 +297,66 @@ void TileBatchQueue::harvest(Slot& slot, bool ok) noexcept
     for (unsigned t = 0; t < workers; ++t) pool.emplace_back(finish, n * t / workers, n * (t + 1) / workers);
     for (std::thread& th : pool) th.join();
   }
-  for (TileDataPtr& tile : slot.tiles) getResultQueue().push(tile);
+  publish(slot.tiles);
   slot.tiles.clear();
 }
 
-void TileBatchQueue::harvestOldest() noexcept
+void TileBatchQueue::harvesterMain() noexcept
 {
-  if (m_inflight.empty()) return;
-  Slot& slot = m_slots[m_inflight.front()];
-  m_inflight.pop_front();
-  tcb200_ctx* ctx = m_gpus[(size_t)slot.gpu].ctx;
-  const bool ok = tcb200_slab_wait(ctx, slot.slab) == TCB200_OK;
-  if (!ok) m_error = tcb200_last_error(ctx);
-  harvest(slot, ok);
-}
-
-void TileBatchQueue::poll() noexcept
-{
-  drainHostResults();
-  while (!m_inflight.empty()) {
-    Slot& slot = m_slots[m_inflight.front()];
-    if (tcb200_slab_ready(m_gpus[(size_t)slot.gpu].ctx, slot.slab) != 1) break;
-    harvestOldest();
+  std::atomic<bool>& stop = m_stop;
+  for (;;) {
+    size_t index;
+    {
+      std::unique_lock<std::mutex> lock(m_flightMutex);
+      m_flightCv.wait(lock, [&] { return !m_inflight.empty() || stop.load(); });
+      if (m_inflight.empty()) return;             // stop requested and nothing in flight
+      index = m_inflight.front();
+      m_inflight.pop_front();
+    }
+    Slot& slot = m_slots[index];
+    tcb200_ctx* ctx = m_gpus[(size_t)slot.gpu].ctx;
+    const bool ok = tcb200_slab_wait(ctx, slot.slab) == TCB200_OK;
+    if (!ok) setError(tcb200_last_error(ctx));
+    finishSlot(slot, ok);
+    { std::lock_guard<std::mutex> lock(m_flightMutex); slot.busy = false; }
+    m_slotFreeCv.notify_all();
   }
 }
 
-TileDataPtr TileBatchQueue::getResult() noexcept
+// ---- host lane: tiles the GPU path does not cover run their own functor on worker threads -----------
+void TileBatchQueue::hostWorker() noexcept
 {
-  poll();
-  if (getResultQueue().empty()) return TileDataPtr();
-  TileDataPtr top = getResultQueue().top();
-  getResultQueue().pop();
-  return top;
+  std::atomic<bool>& stop = m_stop;
+  for (;;) {
+    TileDataPtr tile;
+    {
+      std::unique_lock<std::mutex> lock(m_hostMutex);
+      m_hostWake.wait(lock, [&] { return stop.load() || !m_hostQueue.empty(); });
+      if (m_hostQueue.empty()) return;
+      tile = m_hostQueue.front();
+      m_hostQueue.pop_front();
+      ++m_hostActive;
+    }
+    m_hostSpaceCv.notify_one();
+    (*tile)();                                   // TileData::operator(): encode() or decode() on the CPU
+    { std::lock_guard<std::mutex> lock(m_hostMutex); --m_hostActive; }
+    std::vector<TileDataPtr> one(1, tile);
+    publish(one);
+  }
 }
 
-const TileDataPtr TileBatchQueue::peekResult() noexcept
+void TileBatchQueue::runOnHost(TileDataPtr tile) noexcept
 {
-  poll();
-  return getResultQueue().empty() ? TileDataPtr() : getResultQueue().top();
-}
-
-void TileBatchQueue::waitForResult() noexcept
-{
-  // the caller has nothing more to add right now: ship the partly filled slab, then block until
-  // something is ready or the queue is idle
-  submitCurrent();
-  drainHostResults();
-  if (!getResultQueue().empty()) return;
-  if (!m_inflight.empty()) { harvestOldest(); return; }
-  std::unique_lock<std::mutex> lock(m_hostMutex);
-  m_hostDoneCv.wait(lock, [this] { return !m_hostDone.empty() || (m_hostQueue.empty() && m_hostActive == 0); });
-  while (!m_hostDone.empty()) { getResultQueue().push(m_hostDone.front()); m_hostDone.pop_front(); }
-}
-
-bool TileBatchQueue::finished() noexcept
-{
-  poll();
-  const bool filling = !m_slots.empty() && !m_slots[m_current].tiles.empty();
-  bool hostIdle;
+  if (m_workers.empty())
+    for (unsigned t = 0; t < m_threads; ++t) m_workers.emplace_back(&TileBatchQueue::hostWorker, this);
+  { std::lock_guard<std::mutex> lock(m_doneMutex); ++m_pending; }
   {
-    std::lock_guard<std::mutex> lock(m_hostMutex);
-    hostIdle = m_hostQueue.empty() && m_hostActive == 0 && m_hostDone.empty();
+    // bounded like the reference's input queue (getMaxTiles(), tilethreadpool_posix.cpp:66)
+    std::unique_lock<std::mutex> lock(m_hostMutex);
+    m_hostSpaceCv.wait(lock, [this] { return m_hostQueue.size() < (size_t)std::max(1u, getMaxTiles()); });
+    m_hostQueue.push_back(tile);
   }
-  return !filling && m_inflight.empty() && hostIdle && getResultQueue().empty();
+  m_hostWake.notify_one();
 }
 
 // ---- the two link-time factory functions of tilethreadpool_base.h:38,44 --------------------------
