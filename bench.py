@@ -178,6 +178,32 @@ def as_shipped_cli_rate(pool: np.ndarray, sample: int, type_: int, quality: int)
             "note": "capped by the reference pool's 64-tile window and 50 ms polling sleeps (SURVEY.md F4)"}
 
 
+def pool_seam_rate(tiles: np.ndarray, type_: int, quality: int):
+    """Side measurement: the same tiles through the reference-facing pool seam -- TileBatchQueue behind
+    createThreadPool()'s interface, fed TileData objects the way Graphics::tisToTBC does (three heap buffers
+    per tile, results drained in index order).  The cost of that caller loop is part of the number."""
+    import ctypes
+    path = os.path.join(ROOT, "tileconv_b200", "libtcb200_host.so")
+    if not os.path.exists(path):
+        return None
+    host = ctypes.CDLL(path)
+    n = tiles.shape[0]
+    stride = 2052 if type_ == 1 else 4100
+    out = np.zeros((n, stride), np.uint8)
+    sizes = np.zeros(n, np.int32)
+    args = lambda m: (type_, quality, 0, ctypes.c_void_p(tiles.ctypes.data), None, m, ctypes.c_void_p(out.ctypes.data), stride,
+                      ctypes.c_void_p(sizes.ctypes.data), 4096, 1, 4)
+    host.tcbh_queue_encode(*args(min(n, 8192)))          # warm-up (contexts, pinned slabs, allocator)
+    t0 = time.perf_counter()
+    rc = host.tcbh_queue_encode(*args(n))
+    dt = time.perf_counter() - t0
+    if rc != 0:
+        return None
+    return {"value": n / dt, "unit": "tiles/s", "tiles": n,
+            "path": "TileData objects -> TileBatchQueue (createThreadPool seam) -> ordered results, 1 GPU, -u",
+            "note": "bounded by the single-threaded reference caller loop (per-tile heap buffers + ordered drain), not by the GPU"}
+
+
 def flops_per_tile(per_tile: dict) -> float:
     """W = C3*138 + C4*160 + F_fixed, F_fixed(n) ~ 30 n + 8*27 per cluster block."""
     return (per_tile["cand3"] * F3_OPS + per_tile["cand4"] * F4_OPS
@@ -341,6 +367,7 @@ def main() -> int:
     sample = min(args.cpu_sample, POOL_TILES)
     cpu_rate, cores, kind, per_tile = cpu_reference_rate(pool, sample, args.type, args.quality)
     shipped = as_shipped_cli_rate(pool, min(sample, 1024), args.type, args.quality)
+    seam = pool_seam_rate(tiles[:min(B, 65536)], args.type, args.quality) if world == 1 else None
     # parity of the measured outputs: the first `sample` tiles of the batch are pool tiles (copy 0)
     want = pyoracle.encode_tiles(pool[:256], args.type, args.quality, threads=cores)
     parity_ok = bool(np.array_equal(dev_result[:256], want)) if rank * B == 0 else None
@@ -394,6 +421,7 @@ def main() -> int:
         "cpu_baseline": {"value": cpu_rate, "unit": "tiles/s", "cores": cores, "kind": kind,
                          "sample": f"{sample} pool tiles, {cores} threads over the reference's TileData::encode (-u), restated squish",
                          "as_shipped_cli": shipped},
+        "e2e_pool_seam": seam,
         "parity_spot_check": parity_ok,
         "modes": modes,
     }

@@ -165,6 +165,27 @@ def test_batch_queue_shards_slabs_over_all_gpus(host, oracle):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("slab,threads,deflate", ((5, 1, 0), (33, 4, 1), (257, 3, 0)))
+def test_batch_queue_stress_many_small_slabs(host, oracle, slab, threads, deflate):
+    """Feeder / harvester hand-over under pressure: thousands of tiles through tiny slabs (every slot is
+    recycled hundreds of times), results must come back complete, in order and identical to one big batch."""
+    n = 3000
+    tiles = synth.rotate_palettes(synth.mixed_tiles(n, 192), 3)
+    stride = 4096
+    out = np.zeros((n, stride), np.uint8); sizes = np.zeros(n, np.int32)
+    rc = host.tcbh_queue_encode(1, 2, deflate, p(tiles), None, n, p(out), stride, p(sizes), slab, 0, threads)
+    assert rc == 0, host.tcbh_last_error()
+    from tileconv_b200 import Encoder
+    with Encoder(1, 2) as enc:
+        want = enc.encode(tiles)
+    for i in range(n):
+        got = out[i, :sizes[i]].tobytes()
+        if deflate:
+            got = zlib.decompress(got)
+        assert got == want[i].tobytes(), i
+
+
+@pytest.mark.gpu
 def test_batch_queue_ragged_and_deflated(host, oracle):
     tiles, wh = synth.ragged_tiles(40, 93)
     stride = 8192
