@@ -11,6 +11,11 @@
  * reference interface it stands in for, so that a maintainer can bind it from the reference's
  * Converter / TileThreadPool seams.
  *
+ * Threading: a context may be driven by one thread at a time, with one exception the batch queue relies
+ * on: the slab functions of DIFFERENT slabs may run on different threads concurrently (one thread fills and
+ * submits, another waits and reads), as long as each slab is handed from one thread to the other with a
+ * proper happens-before edge.  Different contexts are independent.
+ *
  * Data layouts (all little-endian, identical to the reference's in-memory tiles):
  *   input tile record  = 5120 bytes: 1024 B palette (256 x {B,G,R,x}) then 4096 B index area.
  *                        A w x h tile (w,h <= 64) keeps its indices in the first w*h bytes with
