@@ -166,6 +166,40 @@ def test_nan_principal_axis_blocks(oracle, type_, quality):
     assert_blocks_equal(got, oracle.encode_tiles(t, type_, quality), type_, "NaN-axis blocks")
 
 
+def black_and_transparent_tiles():
+    """Opaque black pixels and keyed-transparent pixels share the colour (0,0,0) in BC2/BC3, so with
+    kWeightColourByAlpha their weights add up as (256*opaque + transparent)/256 on ONE point (App. A.3);
+    in BC1 the transparent ones leave the set.  Mixed with a few other colours, every ratio 0..16."""
+    rng = np.random.default_rng(17)
+    t = np.zeros((3, 5120), np.uint8)
+    for k in range(3):
+        pal = rng.integers(0, 256, (256, 4), dtype=np.uint8); pal[:, 3] = 0
+        pal[0] = synth.KEY_ENTRY          # index 0: transparent
+        pal[1] = [0, 0, 0, 0]             # index 1: opaque black
+        pal[2] = [0, 0, 0, 0]             # index 2: a second palette entry with the same colour
+        t[k, :1024] = pal.reshape(-1)
+        idx = t[k, 1024:].reshape(64, 64)
+        for by in range(16):
+            for bx in range(16):
+                n_t = (by + k) % 17 if (by + k) % 17 <= 16 else 0
+                cells = rng.permutation(16)
+                vals = np.empty(16, np.uint8)
+                vals[:] = rng.integers(3, 3 + 1 + bx // 2, 16)          # 1..8 other colours
+                vals[cells[:min(n_t, 16)]] = 0
+                n_b = bx % 9
+                vals[cells[min(n_t, 16):min(n_t, 16) + n_b]] = rng.integers(1, 3, min(n_b, 16 - min(n_t, 16)))
+                idx[4 * by:4 * by + 4, 4 * bx:4 * bx + 4] = vals.reshape(4, 4)
+    return t
+
+
+@pytest.mark.parametrize("type_,quality", ((1, 9), (2, 4), (2, 6), (3, 5), (3, 9), (3, 2)))
+def test_black_merges_with_transparent_weights(oracle, type_, quality):
+    t = black_and_transparent_tiles()
+    with encoder(type_, quality) as enc:
+        got = enc.encode(t)
+    assert_blocks_equal(got, oracle.encode_tiles(t, type_, quality, threads=4), type_, "black+transparent")
+
+
 def test_inlined_reciprocal_is_ieee_exact():
     """The cluster solve replaces `1.0f/x` by MUFU.RCP + one Newton step without the compiler's range
     check; every binary32 value of the range the solve can produce must give the IEEE result."""
