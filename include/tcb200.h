@@ -81,7 +81,8 @@ int tcb200_encode(tcb200_ctx* ctx, const uint8_t* tiles, const uint16_t* wh, int
 
 /* Device-resident variant: all three pointers are device pointers on ctx's device; the kernel is
  * enqueued on `stream` (a cudaStream_t passed as void*, NULL = the context's compute stream) and
- * the call returns without synchronising. */
+ * the call returns without synchronising.  d_tiles must be 16-byte aligned (the kernel stages records
+ * with 128-bit loads), d_out 4-byte aligned. */
 int tcb200_encode_device(tcb200_ctx* ctx, const void* d_tiles, const void* d_wh, int n, void* d_out, void* stream);
 
 /* Asynchronous slab interface used by the batch queue (host side of TileThreadPool's role,

@@ -558,6 +558,8 @@ int tcb200_encode_device(tcb200_ctx* ctx, const void* d_tiles, const void* d_wh,
 {
   if (!ctx) return TCB200_E_ARG;
   if (n < 0 || (n > 0 && (!d_tiles || !d_out))) return fail(ctx, TCB200_E_ARG, "tcb200_encode_device: bad argument");
+  if ((reinterpret_cast<uintptr_t>(d_tiles) & 15u) || (reinterpret_cast<uintptr_t>(d_out) & 3u) || (reinterpret_cast<uintptr_t>(d_wh) & 1u))
+    return fail(ctx, TCB200_E_ARG, "tcb200_encode_device: d_tiles must be 16-byte aligned, d_out 4-byte aligned, d_wh 2-byte aligned");
   TCB_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream[0];
   return launch_encode(ctx, (const uint8_t*)d_tiles, (const uint16_t*)d_wh, n, (uint8_t*)d_out, s);
