@@ -200,6 +200,15 @@ def test_black_merges_with_transparent_weights(oracle, type_, quality):
     assert_blocks_equal(got, oracle.encode_tiles(t, type_, quality, threads=4), type_, "black+transparent")
 
 
+@pytest.mark.parametrize("type_,quality", ((1, 2), (1, 4), (1, 9), (3, 9)))
+def test_corner_case_blocks(oracle, type_, quality):
+    """Two-colour, collinear, on-grid, one-LSB-apart, outlier, grey and duplicated-palette blocks."""
+    t = synth.corner_case_tiles(24, 5678)
+    with encoder(type_, quality) as enc:
+        got = enc.encode(t)
+    assert_blocks_equal(got, oracle.encode_tiles(t, type_, quality, threads=16), type_, "corner-case blocks")
+
+
 def test_inlined_reciprocal_is_ieee_exact():
     """The cluster solve replaces `1.0f/x` by MUFU.RCP + one Newton step without the compiler's range
     check; every binary32 value of the range the solve can produce must give the IEEE result."""

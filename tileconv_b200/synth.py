@@ -117,3 +117,52 @@ def ragged_tiles(n: int, seed: int = 4567):
         img = base[t, 1024:].reshape(64, 64)[:h, :w]
         tiles[t, 1024:1024 + w * h] = img.reshape(-1)
     return tiles, wh
+
+
+def corner_case_tiles(n: int, seed: int = 5678) -> np.ndarray:
+    """Blocks built to stress the fitters' numerics rather than their throughput: per 4x4 block one of
+    two colours only / colours on a line in RGB / colours already on the 5:6:5 grid / colours one LSB
+    apart / a single colour with one outlier / 16 greys / duplicated palette entries.  No transparency."""
+    rng = np.random.default_rng(seed)
+    tiles = np.zeros((n, TILE_RECORD), dtype=np.uint8)
+    for t in range(n):
+        pal = np.zeros((256, 3), dtype=np.int64)      # r,g,b
+        idx = np.zeros((64, 64), dtype=np.uint8)
+        used = 0
+        for by in range(16):
+            for bx in range(16):
+                kind = int(rng.integers(0, 7))
+                k = int(rng.integers(2, 9))
+                if kind == 0:      # two colours
+                    cols = rng.integers(0, 256, (2, 3))
+                elif kind == 1:    # collinear
+                    a, d = rng.integers(0, 200, 3), rng.integers(-6, 7, 3)
+                    cols = np.clip(a[None, :] + np.arange(k)[:, None] * d[None, :], 0, 255)
+                elif kind == 2:    # on the 565 grid
+                    r5, g6, b5 = rng.integers(0, 32, k), rng.integers(0, 64, k), rng.integers(0, 32, k)
+                    cols = np.stack([(r5 << 3) | (r5 >> 2), (g6 << 2) | (g6 >> 4), (b5 << 3) | (b5 >> 2)], axis=1)
+                elif kind == 3:    # one LSB apart
+                    a = rng.integers(1, 255, 3)
+                    cols = np.clip(a[None, :] + rng.integers(-1, 2, (k, 3)), 0, 255)
+                elif kind == 4:    # one colour + outlier
+                    cols = np.stack([rng.integers(0, 256, 3), rng.integers(0, 256, 3)])
+                elif kind == 5:    # greys
+                    g = np.sort(rng.integers(0, 256, k))
+                    cols = np.stack([g, g, g], axis=1)
+                else:              # duplicated colours under different palette indices
+                    a = rng.integers(0, 256, (max(1, k // 2), 3))
+                    cols = np.concatenate([a, a])
+                m = len(cols)
+                if used + m > 256:
+                    used = 0       # start overwriting: earlier blocks keep their indices but may change colour (fine)
+                pal[used:used + m] = cols
+                choice = rng.integers(0, m, 16)
+                if kind == 4:
+                    choice[:] = 0; choice[int(rng.integers(0, 16))] = 1
+                idx[4 * by:4 * by + 4, 4 * bx:4 * bx + 4] = (used + choice).reshape(4, 4)
+                used += m
+        tiles[t, 0:1024:4] = pal[:, 2]; tiles[t, 1:1024:4] = pal[:, 1]; tiles[t, 2:1024:4] = pal[:, 0]
+        if tiles[t, 0] == 0 and tiles[t, 1] == 255 and tiles[t, 2] == 0:
+            tiles[t, 1] = 254
+        tiles[t, 1024:] = idx.reshape(-1)
+    return tiles

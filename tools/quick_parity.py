@@ -7,7 +7,8 @@ from oracle import pyoracle
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 16
-    sets = {"S-U": synth.uniform_tiles(n), "S-G": synth.smooth_tiles(n), "S-K": synth.keyed_tiles(n)}
+    sets = {"S-U": synth.uniform_tiles(n), "S-G": synth.smooth_tiles(n), "S-K": synth.keyed_tiles(n),
+            "S-C": synth.corner_case_tiles(n)}
     rag, wh = synth.ragged_tiles(n)
     bad = 0
     for t in (1, 2, 3):
