@@ -4,6 +4,7 @@
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 
 #include <zlib.h>
 
@@ -23,20 +24,30 @@ int pixelTypeOf(const Options& options)
   }
 }
 
-// one-shot zlib stream at level 9 into a buffer of 2x the source size (compress.cpp:36,54-67;
-// tiledata.cpp:142-143); 0 on failure
-uint32_t deflateRecord(const uint8_t* src, uint32_t srcSize, uint8_t* dst, uint32_t dstSize)
+// One-shot zlib streams at level 9 into a buffer of 2x the source size, byte-identical to what the
+// reference produces per tile (compress.cpp:36,54-67; tiledata.cpp:142-143).  The reference builds a
+// fresh Compression object (deflateInit: ~270 KB of state, i.e. an mmap/munmap pair) for every tile; here
+// one stream serves a worker's whole share of a slab and is deflateReset between tiles, which yields the
+// same bytes without the allocator traffic.
+class RecordDeflater
 {
-  z_stream z;
-  std::memset(&z, 0, sizeof(z));
-  if (deflateInit(&z, 9) != Z_OK) return 0;
-  z.avail_in = srcSize; z.next_in = const_cast<Bytef*>(src);
-  z.avail_out = dstSize; z.next_out = dst;
-  const int rc = ::deflate(&z, Z_FINISH);
-  const uint32_t written = dstSize - z.avail_out;
-  deflateEnd(&z);
-  return rc == Z_STREAM_ERROR ? 0 : written;
-}
+public:
+  RecordDeflater() { std::memset(&m_z, 0, sizeof(m_z)); m_ok = deflateInit(&m_z, 9) == Z_OK; }
+  ~RecordDeflater() { if (m_ok) deflateEnd(&m_z); }
+  uint32_t run(const uint8_t* src, uint32_t srcSize, uint8_t* dst, uint32_t dstSize)
+  {
+    if (!m_ok) return 0;
+    m_z.avail_in = srcSize; m_z.next_in = const_cast<Bytef*>(src);
+    m_z.avail_out = dstSize; m_z.next_out = dst;
+    const int rc = ::deflate(&m_z, Z_FINISH);
+    const uint32_t written = dstSize - m_z.avail_out;
+    deflateReset(&m_z);
+    return rc == Z_STREAM_ERROR ? 0 : written;
+  }
+private:
+  z_stream m_z;
+  bool m_ok;
+};
 
 }  // namespace
 
@@ -280,12 +291,13 @@ void TileBatchQueue::finishSlot(Slot& slot, bool ok) noexcept
   const int stride = tcb200_record_stride(ctx);
   const size_t n = slot.tiles.size();
   auto finish = [&](size_t lo, size_t hi) {
+    std::unique_ptr<RecordDeflater> deflater(m_deflate ? new RecordDeflater() : nullptr);
     for (size_t i = lo; i < hi; ++i) {
       TileData& tile = *slot.tiles[i];
       const int size = tcb200_record_size(m_type, tile.getWidth(), tile.getHeight());
       if (out == nullptr || size <= 0) { tile.setSize(0); continue; }
       const uint8_t* record = out + i * (size_t)stride;
-      if (m_deflate) tile.setSize((int)deflateRecord(record, (uint32_t)size, tile.getDeflatedData().get(), (uint32_t)size * 2));
+      if (m_deflate) tile.setSize((int)deflater->run(record, (uint32_t)size, tile.getDeflatedData().get(), (uint32_t)size * 2));
       else { std::memcpy(tile.getDeflatedData().get(), record, (size_t)size); tile.setSize(size); }
     }
   };
