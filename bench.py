@@ -383,12 +383,14 @@ def main() -> int:
     except Exception:
         pass
 
-    traffic = None
+    traffic, ncu_facts = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
             t = json.load(f).get(f"bc{args.type}_q{args.quality}_batch{B}")
         if t:
             traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
+            ncu_facts = {k: t[k] for k in ("smsp_issue_active_pct", "sm_pipe_fma_cycles_active_pct", "active_lanes_per_instruction",
+                                           "dominant_stall") if k in t}
     except Exception:
         pass
 
@@ -414,6 +416,7 @@ def main() -> int:
                      "peak_unfused": peak_unfused / 1e12,
                      "frac_of_unfused": achieved_tflops / (peak_unfused / 1e12),
                      "note": "bit-exactness forbids mul+add fusion, so the attainable ceiling is peak_unfused (separate FMUL/FADD)",
+                     "ncu": ncu_facts,      # from the committed capture of this configuration (profiles/), not measured in this run
                      "flops_per_tile": flops_tile,
                      "candidates_per_tile": {"c3": per_tile["cand3"], "c4": per_tile["cand4"]},
                      "hbm": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
