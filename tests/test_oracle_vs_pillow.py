@@ -37,3 +37,24 @@ def test_pillow_reads_the_same_picture(oracle, type_):
         opaque = want[:, :, 3] > 0
         # interpolated colours may round differently by one step between decoders
         assert np.abs(got[:, :, :3] - want[:, :, :3])[opaque].max() <= 1
+
+
+def test_cluster_fit_beats_an_independent_simple_encoder(oracle):
+    """Sanity of the restated fitters' QUALITY: Pillow ships its own (simple) BC1 encoder; on the same pixels
+    the oracle's RangeFit must not be worse than it by more than a whisker and ClusterFit must be better."""
+    tiles = np.concatenate([synth.smooth_tiles(3, 131), synth.uniform_tiles(2, 132)])
+    for t in tiles:
+        src = oracle.pal_to_argb(t[1024:], t[:1024]).reshape(64, 64, 4)[:, :, [2, 1, 0, 3]]
+        buf = io.BytesIO()
+        try:
+            PIL.fromarray(src.astype(np.uint8), "RGBA").save(buf, format="DDS", pixel_format="DXT1")
+        except Exception as e:       # older Pillow: no DDS writer
+            pytest.skip(f"Pillow cannot write DXT1: {e}")
+        theirs = np.asarray(PIL.open(io.BytesIO(buf.getvalue())).convert("RGBA")).astype(float)
+        rmse_pillow = np.sqrt(((theirs[:, :, :3] - src[:, :, :3]) ** 2).mean())
+        rmse = {}
+        for q in (2, 4, 9):
+            dec = oracle.decode_tile(oracle.encode_tiles(t[None], 1, q)[0], 1)[:, :, [2, 1, 0]].astype(float)
+            rmse[q] = np.sqrt(((dec - src[:, :, :3]) ** 2).mean())
+        assert rmse[9] <= rmse[4] + 1e-9 <= rmse[2] + 1e-9
+        assert rmse[4] < rmse_pillow and rmse[2] < rmse_pillow * 1.05
