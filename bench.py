@@ -351,6 +351,22 @@ def main() -> int:
                 modes[f"bc{t_}_q{q_}"] = {"tiles_per_s": world * B / (ms2 * 1e-3), "ms_per_step": ms2}
                 del d_o2
 
+        # "next" row N3: the BCn decode kernel is the HBM-bound one of the set (2 KB in, 16 KB out per tile)
+        for t_ in (1, 3):
+            with Encoder(t_, 2, device=local_rank, max_batch_tiles=4096) as e3:
+                rec = torch.from_numpy(e3.encode(pool[:2048])).cuda()
+                reps_n = B // 2048
+                d_rec = rec.repeat(reps_n, 1).contiguous()
+                d_pix = torch.empty(reps_n * 2048 * 4096 * 4, dtype=torch.uint8, device="cuda")
+                torch.cuda.synchronize()
+                e3.time_decode_ms(d_rec.data_ptr(), reps_n * 2048, d_pix.data_ptr(), 2)
+                ms3 = max_over_ranks(e3.time_decode_ms(d_rec.data_ptr(), reps_n * 2048, d_pix.data_ptr(), 5))
+                nt = reps_n * 2048
+                gbs = nt * (e3.stride + 16384) / (ms3 * 1e-3) / 1e9
+                modes[f"decode_bc{t_}"] = {"tiles_per_s": world * nt / (ms3 * 1e-3), "ms_per_step": ms3,
+                                           "roofline": {"bound": "hbm", "achieved": gbs, "unit": "GB/s", "bytes_per_tile": e3.stride + 16384}}
+                del d_rec, d_pix, rec
+
     # ---- FP32 peaks measured live (rank 0's GPU) ------------------------------------------------
     peak_fused = enc.fp32_peak(True) * 2.0      # FLOP/s, an FFMA counts 2
     peak_unfused = enc.fp32_peak(False)         # FLOP/s of separate FMUL / FADD
@@ -382,6 +398,10 @@ def main() -> int:
             hbm_peak, hbm_src = float(json.load(f)["hbm_gbs"]), "measured"
     except Exception:
         pass
+
+    for m in modes.values():
+        if "roofline" in m:
+            m["roofline"].update({"peak": hbm_peak, "frac": m["roofline"]["achieved"] / hbm_peak, "peak_source": f"MEASURED_PEAKS.json ({hbm_src})"})
 
     traffic, ncu_facts = None, None
     try:

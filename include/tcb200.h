@@ -118,6 +118,10 @@ int tcb200_pal_to_argb(tcb200_ctx* ctx, const uint8_t* tiles, int n, uint8_t* bg
  * Quantising the pixels back to a palette (Colors::ARGBToPal, libimagequant) stays on the host. */
 int tcb200_decode(tcb200_ctx* ctx, const uint8_t* records, int n, uint8_t* bgra, int reference_bc3_alpha);
 
+/* Kernel-only timing aid for the decode kernel on device-resident records / pixels (same conventions as
+ * tcb200_time_kernel_ms below); mean milliseconds per launch, negative on error. */
+float tcb200_time_decode_ms(tcb200_ctx* ctx, const void* d_records, int n, void* d_bgra, int reference_bc3_alpha, int reps);
+
 /* Kernel-only timing aid for bench.py: runs the encode kernel `reps` times on device-resident data
  * on the context's compute stream and returns the mean milliseconds per launch measured with CUDA
  * events on that stream (negative error code on failure). */

@@ -39,6 +39,7 @@ SYMBOLS = [
     ("tcb200_host_free", None, [ctypes.c_void_p]),
     ("tcb200_pal_to_argb", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     ("tcb200_decode", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]),
+    ("tcb200_time_decode_ms", ctypes.c_float, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
     ("tcb200_time_kernel_ms", ctypes.c_float, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]),
     ("tcb200_fp32_peak", ctypes.c_double, [ctypes.c_void_p, ctypes.c_int]),
     ("tcb200_selftest_reciprocal", ctypes.c_longlong, [ctypes.c_void_p]),
@@ -177,6 +178,12 @@ class Encoder:
         ms = float(self._lib.tcb200_time_kernel_ms(self._ctx, d_tiles, d_wh, n, d_out, reps))
         if ms < 0:
             self._check(int(ms), "tcb200_time_kernel_ms")
+        return ms
+
+    def time_decode_ms(self, d_records: int, n: int, d_bgra: int, reps: int, reference_bc3_alpha: bool = False) -> float:
+        ms = float(self._lib.tcb200_time_decode_ms(self._ctx, d_records, n, d_bgra, 1 if reference_bc3_alpha else 0, reps))
+        if ms < 0:
+            self._check(int(ms), "tcb200_time_decode_ms")
         return ms
 
     def fp32_peak(self, fused: bool) -> float:

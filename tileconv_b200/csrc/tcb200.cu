@@ -242,26 +242,37 @@ decode_tiles_kernel(const uint8_t* __restrict__ records, int ntiles, int stride,
         table[6] = 0u; table[7] = 255u;
       }
       const uint64_t ctrl = v >> 16;
+      // the 8 table bytes live in two registers; PRMT picks byte `idx` of the pair in one instruction
+      const uint32_t tabLo = table[0] | (table[1] << 8) | (table[2] << 16) | (table[3] << 24);
+      const uint32_t tabHi = table[4] | (table[5] << 8) | (table[6] << 16) | (table[7] << 24);
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const uint32_t idx = (uint32_t)(ctrl >> (3 * i)) & 7u;
-        uint32_t a = table[0];
-#pragma unroll
-        for (int k = 1; k < 8; ++k) a = (idx == (uint32_t)k) ? table[k] : a;
-        alpha[i] = a;
+        alpha[i] = __byte_perm(tabLo, tabHi, idx) & 0xffu;
       }
     }
     const int bx = b % bw, by = b / bw;
     uint32_t* dst = bgra + (size_t)tile * 4096;
+    uint32_t px[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-      const int x = 4 * bx + (i & 3), y = 4 * by + (i >> 2);
-      if (x < w && y < h) {
-        const uint32_t code = (codes >> (2 * i)) & 3u;
-        uint32_t px = pal[0];
-        px = code == 1u ? pal[1] : px; px = code == 2u ? pal[2] : px; px = code == 3u ? pal[3] : px;
-        if (TYPE != 1) px = (px & 0x00ffffffu) | (alpha[i] << 24);
-        dst[y * w + x] = px;
+      const uint32_t code = (codes >> (2 * i)) & 3u;
+      uint32_t v = pal[0];
+      v = code == 1u ? pal[1] : v; v = code == 2u ? pal[2] : v; v = code == 3u ? pal[3] : v;
+      if (TYPE != 1) v = (v & 0x00ffffffu) | (alpha[i] << 24);
+      px[i] = v;
+    }
+    if ((w & 3) == 0 && 4 * by + 3 < h) {
+      // whole block inside the tile and rows 16-byte aligned: one 128-bit store per pixel row; a warp
+      // covers 32 consecutive blocks, i.e. 512 contiguous bytes of each of its pixel rows
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        __stcs(reinterpret_cast<uint4*>(dst + (4 * by + r) * w + 4 * bx), make_uint4(px[4 * r], px[4 * r + 1], px[4 * r + 2], px[4 * r + 3]));   // streaming: written once, never re-read here
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int x = 4 * bx + (i & 3), y = 4 * by + (i >> 2);
+        if (x < w && y < h) dst[y * w + x] = px[i];
       }
     }
   }
@@ -701,9 +712,10 @@ int tcb200_decode(tcb200_ctx* ctx, const uint8_t* records, int n, uint8_t* bgra,
     if (e == cudaSuccess) e = cudaMemsetAsync(dPix, 0, (size_t)m * 4096 * 4, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->dOut[0], records + (size_t)first * ctx->stride, (size_t)m * ctx->stride, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) {
-      if (ctx->type == 1) decode_tiles_kernel<1><<<m, kThreads, 0, st>>>(ctx->dOut[0], m, ctx->stride, dPix, reference_bc3_alpha);
-      else if (ctx->type == 2) decode_tiles_kernel<2><<<m, kThreads, 0, st>>>(ctx->dOut[0], m, ctx->stride, dPix, reference_bc3_alpha);
-      else decode_tiles_kernel<3><<<m, kThreads, 0, st>>>(ctx->dOut[0], m, ctx->stride, dPix, reference_bc3_alpha);
+      const int grid = m < ctx->sms * 16 ? m : ctx->sms * 16;      // persistent CTAs: 16 per SM, grid-stride over tiles
+      if (ctx->type == 1) decode_tiles_kernel<1><<<grid, kThreads, 0, st>>>(ctx->dOut[0], m, ctx->stride, dPix, reference_bc3_alpha);
+      else if (ctx->type == 2) decode_tiles_kernel<2><<<grid, kThreads, 0, st>>>(ctx->dOut[0], m, ctx->stride, dPix, reference_bc3_alpha);
+      else decode_tiles_kernel<3><<<grid, kThreads, 0, st>>>(ctx->dOut[0], m, ctx->stride, dPix, reference_bc3_alpha);
       ctx->launches.fetch_add(1);
       e = cudaGetLastError();
     }
@@ -713,6 +725,27 @@ int tcb200_decode(tcb200_ctx* ctx, const uint8_t* records, int n, uint8_t* bgra,
   cudaFree(dPix);
   if (e != cudaSuccess) return fail(ctx, TCB200_E_CUDA, "tcb200_decode", e);
   return TCB200_OK;
+}
+
+float tcb200_time_decode_ms(tcb200_ctx* ctx, const void* d_records, int n, void* d_bgra, int reference_bc3_alpha, int reps)
+{
+  if (!ctx || reps <= 0 || n <= 0 || !d_records || !d_bgra) return (float)TCB200_E_ARG;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return (float)TCB200_E_CUDA;
+  cudaStream_t st = ctx->stream[0];
+  if (cudaEventRecord(ctx->t0, st) != cudaSuccess) return (float)TCB200_E_CUDA;
+  for (int r = 0; r < reps; ++r) {
+    const uint8_t* rec = (const uint8_t*)d_records;
+    uint32_t* pix = (uint32_t*)d_bgra;
+    if (ctx->type == 1) decode_tiles_kernel<1><<<(n < ctx->sms * 16 ? n : ctx->sms * 16), kThreads, 0, st>>>(rec, n, ctx->stride, pix, reference_bc3_alpha);
+    else if (ctx->type == 2) decode_tiles_kernel<2><<<(n < ctx->sms * 16 ? n : ctx->sms * 16), kThreads, 0, st>>>(rec, n, ctx->stride, pix, reference_bc3_alpha);
+    else decode_tiles_kernel<3><<<(n < ctx->sms * 16 ? n : ctx->sms * 16), kThreads, 0, st>>>(rec, n, ctx->stride, pix, reference_bc3_alpha);
+    ctx->launches.fetch_add(1);
+  }
+  if (cudaGetLastError() != cudaSuccess || cudaEventRecord(ctx->t1, st) != cudaSuccess) return (float)TCB200_E_CUDA;
+  if (cudaEventSynchronize(ctx->t1) != cudaSuccess) return (float)TCB200_E_CUDA;
+  float ms = 0.0f;
+  if (cudaEventElapsedTime(&ms, ctx->t0, ctx->t1) != cudaSuccess) return (float)TCB200_E_CUDA;
+  return ms / (float)reps;
 }
 
 float tcb200_time_kernel_ms(tcb200_ctx* ctx, const void* d_tiles, const void* d_wh, int n, void* d_out, int reps)
