@@ -22,7 +22,7 @@ TBC_ENCODE = os.path.join(ROOT, "tileconv_b200", "tbc_encode")
 
 def test_host_library_exports():
     lib = ctypes.CDLL(HOSTLIB)
-    for name in ("tcbh_convert_tile", "tcbh_queue_encode", "tcbh_encode_file", "tcbh_last_error"):
+    for name in ("tcbh_convert_tile", "tcbh_queue_encode", "tcbh_queue_encode_mixed", "tcbh_encode_file", "tcbh_last_error"):
         assert hasattr(lib, name)
 
 
@@ -136,6 +136,23 @@ def test_batch_queue_ordered_results(host, oracle, slab, n):
     with Encoder(1, 9) as enc:
         assert np.array_equal(out, enc.encode(tiles))
     assert np.array_equal(out[:16], oracle.encode_tiles(tiles[:16], 1, 9, threads=8))
+
+
+@pytest.mark.gpu
+def test_batch_queue_tiles_with_different_options(host, oracle):
+    """One pool, tiles that carry different Options (the reference's pool runs whatever functor each
+    tile brings, tilethreadpool_posix.cpp:119-145): the slabs stay bound to the first tile's
+    (type, level); the others go through the per-tile lane and still come back in index order."""
+    n = 90
+    tiles = synth.keyed_tiles(n, 97)
+    stride = oracle.record_size(3)
+    out = np.zeros((n, stride), np.uint8); sizes = np.zeros(n, np.int32)
+    rc = host.tcbh_queue_encode_mixed(3, 2, 1, 5, 3, p(tiles), n, p(out), stride, p(sizes), 16, 2)
+    assert rc == 0, host.tcbh_last_error()
+    alt = np.arange(n) % 3 == 2
+    assert (sizes[~alt] == stride).all() and (sizes[alt] == oracle.record_size(1)).all()
+    assert np.array_equal(out[~alt], oracle.encode_tiles(tiles[~alt], 3, 2, threads=8))
+    assert np.array_equal(out[alt][:, :oracle.record_size(1)], oracle.encode_tiles(tiles[alt], 1, 5, threads=8))
 
 
 @pytest.mark.gpu

@@ -41,16 +41,14 @@ int tcbh_convert_tile(int type, int quality, const uint8_t* palette, const uint8
   return converter->convert(pal, const_cast<uint8_t*>(indexed), encoded, w, h);
 }
 
-// n tiles through createThreadPool()'s queue with the reference's producer/consumer protocol
-// (graphics.cpp:97-147).  sizes[i] receives TileData::getSize(); out record i starts at i*outStride.
-// Returns 0 when every tile came back, in index order, without error.
-int tcbh_queue_encode(int type, int quality, int deflate, const uint8_t* tiles, const uint16_t* wh, int n,
-                      uint8_t* out, int outStride, int* sizes, int slabTiles, int gpus, int threads)
+}  // extern "C"
+
+namespace {
+
+// tile i carries `options` unless altEvery > 0 and i % altEvery == altEvery - 1, which carries `alt`
+int queueEncode(const Options& options, const Options& alt, int altEvery, const uint8_t* tiles, const uint16_t* wh, int n,
+                uint8_t* out, int outStride, int* sizes, int slabTiles, int gpus, int threads)
 {
-  Options options;
-  options.setEncoding(encodingOf(type));
-  options.setEncodingQuality(quality);
-  options.setDeflate(deflate != 0);
   TileBatchQueue pool((unsigned)(threads > 0 ? threads : 1), 64, slabTiles > 0 ? slabTiles : 4096, gpus);
   int added = 0, drained = 0, problems = 0;
   typedef std::chrono::steady_clock Clock;
@@ -65,10 +63,11 @@ int tcbh_queue_encode(int type, int quality, int deflate, const uint8_t* tiles, 
       BytePtr deflated(new uint8_t[4096 * 4 * 2], std::default_delete<uint8_t[]>());
       std::memcpy(palette.get(), tiles + (size_t)added * 5120, 1024);
       std::memcpy(indexed.get(), tiles + (size_t)added * 5120 + 1024, (size_t)(w > 0 && h > 0 && w <= 64 && h <= 64 ? w * h : 0));
-      TileDataPtr tile(new TileData(options));
+      const Options& mine = (altEvery > 0 && added % altEvery == altEvery - 1) ? alt : options;
+      TileDataPtr tile(new TileData(mine));
       tile->setEncoding(true);
       tile->setIndex(added);
-      tile->setType(Options::GetEncodingCode(options.getEncoding(), options.isDeflate()));
+      tile->setType(Options::GetEncodingCode(mine.getEncoding(), mine.isDeflate()));
       tile->setPaletteData(palette); tile->setIndexedData(indexed); tile->setDeflatedData(deflated);
       tile->setWidth(w); tile->setHeight(h);
       Clock::time_point t1 = Clock::now();
@@ -92,6 +91,33 @@ int tcbh_queue_encode(int type, int quality, int deflate, const uint8_t* tiles, 
   if (profile) std::fprintf(stderr, "tcbh_queue_encode n=%d: make %.1f ms, addTileData %.1f ms, drain %.1f ms, wait %.1f ms\n", n, tMake * 1e3, tAdd * 1e3, tDrain * 1e3, tWait * 1e3);
   t_error = pool.lastError();
   return problems + (n - drained);
+}
+
+}  // namespace
+
+extern "C" {
+
+// n tiles through createThreadPool()'s queue with the reference's producer/consumer protocol
+// (graphics.cpp:97-147).  sizes[i] receives TileData::getSize(); out record i starts at i*outStride.
+// Returns 0 when every tile came back, in index order, without error.
+int tcbh_queue_encode(int type, int quality, int deflate, const uint8_t* tiles, const uint16_t* wh, int n,
+                      uint8_t* out, int outStride, int* sizes, int slabTiles, int gpus, int threads)
+{
+  Options options;
+  options.setEncoding(encodingOf(type));
+  options.setEncodingQuality(quality);
+  options.setDeflate(deflate != 0);
+  return queueEncode(options, options, 0, tiles, wh, n, out, outStride, sizes, slabTiles, gpus, threads);
+}
+
+// Same, but every altEvery-th tile asks for (type2, quality2): one pool fed by tiles with different options.
+int tcbh_queue_encode_mixed(int type, int quality, int type2, int quality2, int altEvery, const uint8_t* tiles, int n,
+                            uint8_t* out, int outStride, int* sizes, int slabTiles, int threads)
+{
+  Options options, alt;
+  options.setEncoding(encodingOf(type)); options.setEncodingQuality(quality); options.setDeflate(false);
+  alt.setEncoding(encodingOf(type2)); alt.setEncodingQuality(quality2); alt.setDeflate(false);
+  return queueEncode(options, alt, altEvery, tiles, nullptr, n, out, outStride, sizes, slabTiles, 0, threads);
 }
 
 // tileconv -t <type> -q -<quality> [-u] [-T] in -> out, encode direction only.

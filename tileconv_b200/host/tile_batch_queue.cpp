@@ -162,6 +162,14 @@ void TileBatchQueue::addTileData(TileDataPtr tileData) noexcept
   const int w = tileData->getWidth(), h = tileData->getHeight();
   const bool valid = tileData->getPaletteData() != nullptr && tileData->getIndexedData() != nullptr &&
                      tileData->getDeflatedData() != nullptr && tileData->getIndex() >= 0 && w > 0 && h > 0 && w <= 64 && h <= 64;
+  if (valid && !m_gpus.empty() &&
+      (pixelTypeOf(tileData->getOptions()) != m_type || tileData->getOptions().getEncodingQuality() != m_quality ||
+       tileData->getOptions().isDeflate() != m_deflate)) {
+    // the slabs are bound to the first tile's (type, level, framing); a tile that asks for something else
+    // runs its own functor, which reaches the GPU one tile at a time through the converter plugin
+    runOnHost(tileData);
+    return;
+  }
   if (!valid || !ensureContexts(tileData->getOptions())) {
     // the reference reports a failed tile through size 0 (graphics.cpp:1140 refuses to write it)
     tileData->setSize(0);
