@@ -63,6 +63,31 @@ int tcb200_record_size(int type, int width, int height);
 tcb200_ctx* tcb200_create(int device, int type, int quality, int max_batch_tiles);
 void        tcb200_destroy(tcb200_ctx* ctx);
 
+/* libsquish-version knobs.  The reference links whatever libsquish the builder dropped into ./squish
+ * (tileconv/Makefile:10, tileconv/squish/remove.me) and calls squish::Compress(rgba, block, flags)
+ * without a metric (tileconv/converter_dxt.cpp:221), so the arithmetic behind that call depends on the
+ * libsquish build a deployment used.  tcb200_create() fixes the choice "libsquish 1.15, scalar
+ * simd_float.h": metric (1,1,1), Reciprocal = 1.0f/x.  tcb200_create_ex() can match the other builds:
+ *   metric      weights of the colour error; (1,1,1) is what libsquish >= 1.11 uses for metric == NULL,
+ *               (0.2126, 0.7152, 0.0722) is the kColourMetricPerceptual default of libsquish <= 1.10.
+ *   reciprocal  TCB200_RECIP_IEEE: scalar build (SQUISH_USE_SSE 0).  TCB200_RECIP_SSE: simd_sse.h
+ *               semantics (SQUISH_USE_SSE 1/2) -- Reciprocal = rcpps estimate + one Newton step in the
+ *               power iteration and the cluster solve, Min/Max like minps/maxps, Truncate like
+ *               cvttps2dq.  The estimate is measured from the HOST CPU's rcpps at create time, i.e. the
+ *               result equals a libsquish SSE build running on this machine.
+ * opt == NULL is tcb200_create().  Measured distance between the variants: profiles/r2_variant_sensitivity.md. */
+#define TCB200_RECIP_IEEE 0
+#define TCB200_RECIP_SSE  1
+typedef struct tcb200_options
+{
+  uint32_t struct_size;      /* sizeof(tcb200_options) */
+  float    metric[3];        /* r, g, b weights, finite and >= 0 */
+  int32_t  reciprocal;       /* TCB200_RECIP_* */
+} tcb200_options;
+void        tcb200_default_options(tcb200_options* opt);
+tcb200_ctx* tcb200_create_ex(int device, int type, int quality, int max_batch_tiles, const tcb200_options* opt);
+int         tcb200_get_options(const tcb200_ctx* ctx, tcb200_options* opt);
+
 /* Last error message of this context (or of the failed tcb200_create when ctx == NULL). */
 const char* tcb200_last_error(const tcb200_ctx* ctx);
 
@@ -84,6 +109,13 @@ int tcb200_encode(tcb200_ctx* ctx, const uint8_t* tiles, const uint16_t* wh, int
  * the call returns without synchronising.  d_tiles must be 16-byte aligned (the kernel stages records
  * with 128-bit loads), d_out 4-byte aligned. */
 int tcb200_encode_device(tcb200_ctx* ctx, const void* d_tiles, const void* d_wh, int n, void* d_out, void* stream);
+
+/* d_wh lives in device memory, so tcb200_encode_device cannot validate it up front the way the host entry
+ * points do: the kernel rejects a record whose w or h is outside 1..64 (it writes a zero {w,h} header and
+ * no blocks, the rest of that output record is untouched) and counts it.  This call waits for the
+ * context's own streams and returns the number of records rejected since the context was created
+ * (0 = none), negative on error.  Work enqueued on a caller-supplied stream must be synchronised by the caller first. */
+long long tcb200_rejected_tiles(tcb200_ctx* ctx);
 
 /* Asynchronous slab interface used by the batch queue (host side of TileThreadPool's role,
  * tileconv/tilethreadpool_base.h:64-81): the context owns `slabs` pinned input/output slabs of
@@ -137,6 +169,11 @@ double tcb200_fp32_peak(tcb200_ctx* ctx, int fused);
  * least-squares denominators): compares it with IEEE 1.0f/x for every binary32 value of magnitude
  * 2^-44 .. 2^10, both signs, and +0.  Returns the number of mismatches (0 = bit-exact), negative on error. */
 long long tcb200_selftest_reciprocal(tcb200_ctx* ctx);
+
+/* Device self-test of the TCB200_RECIP_SSE estimate: estimates[i] = the value the kernels use in place of
+ * the host's rcpps(values[i]) (both host arrays of n floats).  The context must have been created with
+ * TCB200_RECIP_SSE.  The tests compare the result with the CPU instruction itself. */
+int tcb200_selftest_rcpps(tcb200_ctx* ctx, const float* values, int n, float* estimates);
 
 /* Kernels launched by this context so far (bench.py's gpu_launches). */
 long long tcb200_launch_count(const tcb200_ctx* ctx);

@@ -191,3 +191,40 @@ def ref_encode_tiles(tiles: np.ndarray, type_: int, quality: int, threads: int) 
     if failed:
         raise RuntimeError(f"reference failed on {failed} tiles")
     return out
+
+
+PERCEPTUAL = (0.2126, 0.7152, 0.0722)   # libsquish <= 1.10's default metric (kColourMetricPerceptual)
+
+
+def set_variant(metric=None, sse: bool = False) -> None:
+    """libsquish-version knobs of the restated squish (squish_oracle.cpp header): the metric used when
+    the caller passes none, and the SQUISH_USE_SSE arithmetic.  Applies to libtco.so and, when built,
+    to the copy linked into oracle/_ref.  set_variant() restores the oracle's definition."""
+    m = (ctypes.c_float * 3)(*metric) if metric is not None else None
+    oracle().squish_oracle_set_variant(m, 1 if sse else 0)
+    ref = reference()
+    if ref is not None:
+        ref.squish_oracle_set_variant(m, 1 if sse else 0)
+
+
+class variant:
+    """with pyoracle.variant(metric=pyoracle.PERCEPTUAL, sse=True): ..."""
+
+    def __init__(self, metric=None, sse: bool = False):
+        self.metric, self.sse = metric, sse
+
+    def __enter__(self):
+        set_variant(self.metric, self.sse)
+        return self
+
+    def __exit__(self, *exc):
+        set_variant(None, False)
+        return False
+
+
+def rcp_estimate(values: np.ndarray) -> np.ndarray:
+    """The host CPU's rcpps estimate of each float32 in `values`."""
+    fn = oracle().squish_oracle_rcp_estimate
+    fn.restype = ctypes.c_float
+    fn.argtypes = [ctypes.c_float]
+    return np.array([fn(float(v)) for v in np.asarray(values, np.float32).ravel()], np.float32)

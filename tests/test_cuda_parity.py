@@ -3,6 +3,8 @@ against the CPU oracle on the same seeded inputs.  The bar is bit-exact for EVER
 cluster sweeps keep the reference's summation order (prefix sums built left to right, arg-min with
 lowest-candidate tie-break), so the north_star's 99.9 % allowance for ClusterFit is not needed:
 the tests demand 100 % identical blocks and therefore zero RMSE drift."""
+import os
+
 import numpy as np
 import pytest
 
@@ -10,6 +12,8 @@ from conftest import QUALITY_CLASSES
 from tileconv_b200 import synth
 
 pytestmark = pytest.mark.gpu
+
+HOST_THREADS = os.cpu_count() or 8
 
 
 def encoder(type_, quality, **kw):
@@ -27,7 +31,7 @@ def assert_blocks_equal(got, want, type_, what):
 
 
 @pytest.mark.parametrize("type_", (1, 2, 3))
-@pytest.mark.parametrize("quality", (0,) + QUALITY_CLASSES)
+@pytest.mark.parametrize("quality", tuple(range(10)))     # every -q level, incl. 1 and 8
 def test_bit_exact_on_seeded_tiles(oracle, type_, quality):
     sets = {"S-U": synth.uniform_tiles(6, 41), "S-G": synth.smooth_tiles(10, 42), "S-K": synth.keyed_tiles(8, 43)}
     with encoder(type_, quality) as enc:
@@ -54,9 +58,9 @@ def test_config1_bc1_q9_1024_tiles(oracle):
     tiles = synth.mixed_tiles(1024, 1234)
     with encoder(1, 9) as enc:
         got = enc.encode(tiles)
-    want = oracle.encode_tiles(tiles[:192], 1, 9, threads=16)
-    assert_blocks_equal(got[:192], want, 1, "config 1 (first 192 tiles)")
-    # the rest through a size-independent property: byte-different copies with identical pixels
+    want = oracle.encode_tiles(tiles, 1, 9, threads=HOST_THREADS)
+    assert_blocks_equal(got, want, 1, "config 1 (all 1024 tiles)")
+    # and a size-independent property: byte-different copies with identical pixels
     rot = synth.rotate_palettes(tiles, 91)
     with encoder(1, 9) as enc:
         assert np.array_equal(enc.encode(rot), got)
@@ -72,27 +76,26 @@ def test_config2_bc1_q2_bit_exact_1024_tiles(oracle):
 
 def test_config3_bc3_q7_keyed(oracle):
     """BASELINE configs[2]: alpha-keyed palette entry, BC3 with alpha-weighted iterative ClusterFit."""
-    tiles = synth.keyed_tiles(96, 3456)
+    tiles = synth.keyed_tiles(1024, 3456)
     with encoder(3, 7) as enc:
         got = enc.encode(tiles)
-    assert_blocks_equal(got, oracle.encode_tiles(tiles, 3, 7, threads=16), 3, "config 3")
+    assert_blocks_equal(got, oracle.encode_tiles(tiles, 3, 7, threads=HOST_THREADS), 3, "config 3 (all 1024 tiles)")
     # KA7: every BC3 alpha half starts 00 05 (SURVEY App. B)
     blocks = got[:, 4:].reshape(len(tiles), 256, 16)
     assert (blocks[:, :, 0] == 0).all() and (blocks[:, :, 1] == 5).all()
 
 
 def test_config4_large_mos_bc2_q9(oracle):
-    """BASELINE configs[3]: 5120x3840 area map = 80x60 = 4800 full tiles, BC2 -q 9.  A sample is
-    compared with the oracle; the whole map is checked through properties (determinism across
-    chunkings, alpha halves from the closed form KA6)."""
+    """BASELINE configs[3]: 5120x3840 area map = 80x60 = 4800 full tiles, BC2 -q 9.  All 4800 tiles are
+    compared with the oracle, plus properties of the whole map (determinism across chunkings, alpha
+    halves from the closed form KA6)."""
     tiles = np.concatenate([synth.smooth_tiles(3600, 4001), synth.keyed_tiles(1200, 4002)])
     with encoder(2, 9, max_batch_tiles=1000) as enc:
         got = enc.encode(tiles)
     with encoder(2, 9, max_batch_tiles=4800) as enc:
         again = enc.encode(tiles)
     assert np.array_equal(got, again)
-    pick = np.r_[0:24, 3600:3624]
-    assert_blocks_equal(got[pick], oracle.encode_tiles(tiles[pick], 2, 9, threads=16), 2, "config 4 sample")
+    assert_blocks_equal(got, oracle.encode_tiles(tiles, 2, 9, threads=HOST_THREADS), 2, "config 4 (all 4800 tiles)")
     # KA6 on the whole map: alpha nibble F for opaque, 0 for keyed pixels
     px_alpha = np.ones((4800, 64, 64), bool)
     px_alpha[3600:] = tiles[3600:, 1024:].reshape(-1, 64, 64) != 0
@@ -283,3 +286,84 @@ def test_decode_matches_restated_reference_decoder(oracle, type_):
                 assert np.array_equal(px_r[i, :w * h].reshape(h, w, 4), want), (i, w, h, quirk)
             for i in range(len(full)):
                 assert np.array_equal(px_f[i].reshape(64, 64, 4), oracle.decode_tile(rec_f[i], type_, quirk))
+
+
+# ---- libsquish-version knobs (tcb200_create_ex) ---------------------------------------------------------
+VARIANTS = {"perceptual": dict(metric=(0.2126, 0.7152, 0.0722)), "sse": dict(sse=True),
+            "perceptual+sse": dict(metric=(0.2126, 0.7152, 0.0722), sse=True), "odd-metric": dict(metric=(0.5, 1.0, 0.25))}
+
+
+@pytest.mark.parametrize("variant", sorted(VARIANTS))
+@pytest.mark.parametrize("type_,quality", ((1, 2), (1, 4), (1, 9), (2, 9), (3, 6), (3, 8)))
+def test_variants_bit_exact_with_the_oracle_in_the_same_variant(oracle, variant, type_, quality):
+    """The metric and SSE-reciprocal knobs select another libsquish build's arithmetic; the CUDA path must
+    follow the oracle configured the same way, block for block (the SSE estimate is the host CPU's own
+    rcpps on both sides)."""
+    kw = VARIANTS[variant]
+    sets = {"S-U": synth.uniform_tiles(6, 141), "S-G": synth.smooth_tiles(8, 142), "S-K": synth.keyed_tiles(8, 143),
+            "S-C": synth.corner_case_tiles(6, 144), "NaN-axis": nan_axis_tile()}
+    with encoder(type_, quality, **kw) as enc:
+        opt = enc.options()
+        assert opt.reciprocal == (1 if kw.get("sse") else 0)
+        with oracle.variant(**kw):
+            for name, tiles in sets.items():
+                got = enc.encode(tiles)
+                want = oracle.encode_tiles(tiles, type_, quality, threads=8)
+                assert_blocks_equal(got, want, type_, f"{variant} BC{type_} -q{quality} {name}")
+    # and the knobs must actually change something on the GPU side too (S-U at a cluster level)
+    if quality >= 3 and "metric" in kw:
+        with encoder(type_, quality) as enc:
+            base = enc.encode(sets["S-U"])
+        with encoder(type_, quality, **kw) as enc:
+            assert not np.array_equal(enc.encode(sets["S-U"]), base)
+
+
+def test_default_options_are_the_plain_create(oracle):
+    tiles = synth.mixed_tiles(8, 151)
+    with encoder(1, 9) as a, encoder(1, 9, metric=(1.0, 1.0, 1.0)) as b:
+        assert np.array_equal(a.encode(tiles), b.encode(tiles))
+        assert list(b.options().metric) == [1.0, 1.0, 1.0] and b.options().reciprocal == 0
+
+
+def test_rcpps_estimate_matches_the_host_instruction(oracle):
+    """TCB200_RECIP_SSE replaces the host's rcpps by a table measured at create time; compare it with the
+    instruction itself over every exponent, a dense mantissa sample, both signs and the special values."""
+    rng = np.random.default_rng(7)
+    bits = np.concatenate([
+        rng.integers(0, 1 << 32, 200000, dtype=np.uint64).astype(np.uint32),
+        (np.arange(0, 256, dtype=np.uint32)[:, None] << 23 | rng.integers(0, 1 << 23, (256, 64), dtype=np.uint32)).ravel(),
+        (np.uint32(0x3f800000) | np.arange(0, 1 << 23, 257, dtype=np.uint32)),
+        np.array([0, 0x80000000, 0x7f800000, 0xff800000, 1, 0x007fffff, 0x00800000, 0x7f7fffff, 0x7e800000, 0x7e800001], np.uint32)])
+    vals = bits.view(np.float32)
+    with encoder(1, 9, sse=True) as enc:
+        got = enc.selftest_rcpps(vals)
+    want = oracle.rcp_estimate(vals)
+    nan = np.isnan(vals)
+    assert np.isnan(got[nan]).all() and np.isnan(want[nan]).all()
+    assert np.array_equal(got[~nan].view(np.uint32), want[~nan].view(np.uint32))
+
+
+def test_encode_device_rejects_bad_tile_sizes(oracle):
+    """d_wh lives on the device, so tcb200_encode_device cannot validate it: the kernel must neither read nor
+    write out of bounds for w/h outside 1..64, and the context must report the rejected records."""
+    import torch
+    tiles = synth.keyed_tiles(6, 161)
+    wh = np.array([[64, 64], [0, 7], [65, 64], [64, 65535], [3, 5], [64, 64]], np.uint16)
+    for type_, quality in ((1, 9), (3, 2)):
+        with encoder(type_, quality) as enc:
+            good = [0, 4, 5]
+            want = enc.encode(tiles[good], wh[good])
+            d_in = torch.from_numpy(tiles.reshape(-1)).cuda()
+            d_wh = torch.from_numpy(wh.view(np.int16).reshape(-1)).cuda()
+            d_out = torch.full((6 * enc.stride,), 0xAB, dtype=torch.uint8, device="cuda")
+            torch.cuda.synchronize()
+            enc.encode_device(d_in.data_ptr(), d_wh.data_ptr(), 6, d_out.data_ptr())
+            assert enc.rejected_tiles() == 3
+            out = d_out.cpu().numpy().reshape(6, enc.stride)
+            for k, i in enumerate(good):
+                size = oracle.record_size(type_, int(wh[i, 0]), int(wh[i, 1]))
+                assert np.array_equal(out[i, :size], want[k, :size])
+            for i in (1, 2, 3):
+                assert (out[i, :4] == 0).all() and (out[i, 4:] == 0xAB).all()
+            enc.encode_device(d_in.data_ptr(), None, 6, d_out.data_ptr())
+            assert enc.rejected_tiles() == 3

@@ -14,12 +14,27 @@ _LIB: Optional[ctypes.CDLL] = None
 _u8p = ctypes.POINTER(ctypes.c_uint8)
 _u16p = ctypes.POINTER(ctypes.c_uint16)
 
+
+
+class Options(ctypes.Structure):
+    """tcb200_options (include/tcb200.h): the libsquish-version knobs."""
+    _fields_ = [("struct_size", ctypes.c_uint32), ("metric", ctypes.c_float * 3), ("reciprocal", ctypes.c_int32)]
+
+
+RECIP_IEEE, RECIP_SSE = 0, 1
+PERCEPTUAL = (0.2126, 0.7152, 0.0722)   # libsquish <= 1.10's default metric
+
 # (name, restype, argtypes) for every symbol include/tcb200.h declares.
 SYMBOLS = [
     ("tcb200_device_count", ctypes.c_int, []),
     ("tcb200_record_size", ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     ("tcb200_create", ctypes.c_void_p, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     ("tcb200_destroy", None, [ctypes.c_void_p]),
+    ("tcb200_default_options", None, [ctypes.POINTER(Options)]),
+    ("tcb200_create_ex", ctypes.c_void_p, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(Options)]),
+    ("tcb200_get_options", ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Options)]),
+    ("tcb200_rejected_tiles", ctypes.c_longlong, [ctypes.c_void_p]),
+    ("tcb200_selftest_rcpps", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     ("tcb200_last_error", ctypes.c_char_p, [ctypes.c_void_p]),
     ("tcb200_type", ctypes.c_int, [ctypes.c_void_p]),
     ("tcb200_quality", ctypes.c_int, [ctypes.c_void_p]),
@@ -114,9 +129,19 @@ class PinnedBuffer:
 class Encoder:
     """One tcb200_ctx: device x pixel type (1,2,3 = BC1,BC2,BC3) x encode quality (0..9)."""
 
-    def __init__(self, type_: int = 1, quality: int = 9, device: int = 0, max_batch_tiles: int = 0):
+    def __init__(self, type_: int = 1, quality: int = 9, device: int = 0, max_batch_tiles: int = 0,
+                 metric=None, sse: bool = False):
+        """metric / sse: the libsquish-version knobs of tcb200_create_ex (None / False = tcb200_create)."""
         self._lib = load_library()
-        self._ctx = self._lib.tcb200_create(device, type_, quality, max_batch_tiles)
+        if metric is None and not sse:
+            self._ctx = self._lib.tcb200_create(device, type_, quality, max_batch_tiles)
+        else:
+            opt = Options()
+            self._lib.tcb200_default_options(ctypes.byref(opt))
+            if metric is not None:
+                opt.metric[0], opt.metric[1], opt.metric[2] = (float(v) for v in metric)
+            opt.reciprocal = RECIP_SSE if sse else RECIP_IEEE
+            self._ctx = self._lib.tcb200_create_ex(device, type_, quality, max_batch_tiles, ctypes.byref(opt))
         if not self._ctx:
             msg = self._lib.tcb200_last_error(None)
             raise TcbError((msg or b"tcb200_create failed").decode())
@@ -200,6 +225,23 @@ class Encoder:
 
     def launch_count(self) -> int:
         return int(self._lib.tcb200_launch_count(self._ctx))
+
+    def options(self) -> Options:
+        opt = Options()
+        self._check(self._lib.tcb200_get_options(self._ctx, ctypes.byref(opt)), "tcb200_get_options")
+        return opt
+
+    def rejected_tiles(self) -> int:
+        v = int(self._lib.tcb200_rejected_tiles(self._ctx))
+        if v < 0:
+            self._check(v, "tcb200_rejected_tiles")
+        return v
+
+    def selftest_rcpps(self, values: np.ndarray) -> np.ndarray:
+        values = np.ascontiguousarray(values, dtype=np.float32).ravel()
+        out = np.zeros_like(values)
+        self._check(self._lib.tcb200_selftest_rcpps(self._ctx, _ptr(values), values.size, _ptr(out)), "tcb200_selftest_rcpps")
+        return out
 
     # -- expand stage ---------------------------------------------------------------------------
     def pal_to_argb(self, tiles: np.ndarray) -> np.ndarray:

@@ -7,12 +7,15 @@
 #include "../../include/tcb200.h"
 
 #include <atomic>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
 #include <string>
+#include <vector>
+#include <xmmintrin.h>
 
 namespace tcb {
 
@@ -24,10 +27,14 @@ enum Mode { kRange = 0, kCluster = 1, kIterative = 2 };
 template <int TYPE> struct BlockWords { static constexpr int value = (TYPE == 1) ? 2 : 4; };
 
 // One CTA = one tile.  See bc_device.cuh for the phase structure.
-template <int TYPE, bool WEIGHT_ALPHA, int MODE>
+// VARIANT = false: the oracle's definition of the arithmetic, hard-wired (vp unused).  VARIANT = true:
+// metric / SSE-reciprocal knobs read from vp (tcb200_create_ex).  badTiles counts records whose
+// {w,h} is outside 1..64 (only reachable through tcb200_encode_device; the host entry points validate
+// before upload); such a tile gets a zero header and no blocks.
+template <int TYPE, bool WEIGHT_ALPHA, int MODE, bool VARIANT>
 __global__ void __launch_bounds__(kThreads, 4)
 encode_tiles_kernel(const uint8_t* __restrict__ tiles, const uint16_t* __restrict__ wh, int ntiles,
-                    uint8_t* __restrict__ out, int outStride)
+                    uint8_t* __restrict__ out, int outStride, const Variant vp, unsigned* __restrict__ badTiles)
 {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   typedef TileShared<TYPE> Tile;
@@ -51,6 +58,13 @@ encode_tiles_kernel(const uint8_t* __restrict__ tiles, const uint16_t* __restric
     }
     int w = 64, h = 64;
     if (wh != nullptr) { w = wh[2 * tile]; h = wh[2 * tile + 1]; }
+    if (w < 1 || w > 64 || h < 1 || h > 64) {      // uniform across the CTA
+      if (tid == 0) {
+        if (badTiles != nullptr) atomicAdd(badTiles, 1u);
+        *reinterpret_cast<uint32_t*>(out + (size_t)tile * outStride) = 0u;
+      }
+      continue;
+    }
     __syncthreads();
 
     const int bw = (w + 3) >> 2, bh = (h + 3) >> 2, nblocks = bw * bh;
@@ -76,12 +90,12 @@ encode_tiles_kernel(const uint8_t* __restrict__ tiles, const uint16_t* __restric
         dstColour[0] = c.x; dstColour[1] = c.y;
       } else if (MODE == kRange || s.count == 0) {
         float axis[3] = { 0.0f, 0.0f, 0.0f };
-        if (s.count > 0) principal_axis<WEIGHT_ALPHA>(T, jobs, lane, s.count, s.transparent, axis);
-        uint2 c = range_fit_block<TYPE>(T, jobs, lane, s, axis);
+        if (s.count > 0) principal_axis<WEIGHT_ALPHA, VARIANT>(T, jobs, lane, s.count, s.transparent, axis, vp);
+        uint2 c = range_fit_block<TYPE, VARIANT>(T, jobs, lane, s, axis, vp);
         dstColour[0] = c.x; dstColour[1] = c.y;
       } else {
         float axis[3];
-        principal_axis<WEIGHT_ALPHA>(T, jobs, lane, s.count, s.transparent, axis);
+        principal_axis<WEIGHT_ALPHA, VARIANT>(T, jobs, lane, s.count, s.transparent, axis, vp);
         jobs.axis[0][lane] = axis[0]; jobs.axis[1][lane] = axis[1]; jobs.axis[2][lane] = axis[2];
         jobs.remapLo[lane] = s.remapLo; jobs.remapHi[lane] = s.remapHi;
         jobs.mask[lane] = (uint16_t)(TYPE == 1 ? s.disabled : s.transparent);
@@ -125,16 +139,16 @@ encode_tiles_kernel(const uint8_t* __restrict__ tiles, const uint16_t* __restric
             construct_ordering(sc, lane, n, x, y, z, wgt, principle[0], principle[1], principle[2], 0);
             EarlySweep early;
             const uint32_t* cand4 = g_tables.cand + g_tables.off4[n];
-            early.r = run_sweep<4>(sc, lane, n, cand4, g_tables.cnt4[n]);
+            early.r = run_sweep<4, VARIANT>(sc, lane, n, cand4, g_tables.cnt4[n], vp);
             early.entry = 0u;
-            if (early.r.c != kNoCandidate) early.entry = sweep_endpoints<4>(sc, n, cand4, early.r.c, early.win);
-            cluster_fit<3>(sc, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, true, nullptr, best);
-            cluster_fit<4>(sc, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, true, &early, best);
+            if (early.r.c != kNoCandidate) early.entry = sweep_endpoints<4, VARIANT>(sc, n, cand4, early.r.c, early.win, vp);
+            cluster_fit<3, VARIANT>(sc, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, true, nullptr, best, vp);
+            cluster_fit<4, VARIANT>(sc, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, true, &early, best, vp);
           } else {
-            cluster_fit<3>(sc, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, false, nullptr, best);
+            cluster_fit<3, VARIANT>(sc, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, false, nullptr, best, vp);
           }
         } else {
-          cluster_fit<4>(sc, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, false, nullptr, best);
+          cluster_fit<4, VARIANT>(sc, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, false, nullptr, best, vp);
         }
         if (lane == 0) {
           uint32_t* dstColour = T.out + 1 + kWords * ticket + (TYPE == 1 ? 0 : 2);
@@ -314,6 +328,13 @@ __global__ void __launch_bounds__(256) reciprocal_selftest_kernel(unsigned first
   if (bad) atomicAdd(mismatches, bad);
 }
 
+// In place: v[i] := the rcpps estimate the TCB200_RECIP_SSE kernels compute for v[i].
+__global__ void __launch_bounds__(256) rcpps_selftest_kernel(float* v, int n, const Variant vp)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = rcpps_estimate(v[i], vp);
+}
+
 // ================================================================================================
 // host: read-only tables
 // ================================================================================================
@@ -414,6 +435,12 @@ struct tcb200_ctx
   uint8_t* hIn[kSlabs] = {}; uint16_t* hWh[kSlabs] = {}; uint8_t* hOut[kSlabs] = {};
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   std::atomic<long long> launches{0};
+  // libsquish-version knobs (tcb200_create_ex); general == false selects the hard-wired default kernels
+  bool general = false;
+  Variant variant = { { 1.0f, 1.0f, 1.0f }, 0, nullptr, 0 };
+  uint32_t* dRcp = nullptr;
+  unsigned* dBadTiles = nullptr;         // tiles the kernels rejected for their {w,h} (tcb200_encode_device)
+  mutable std::mutex errorMutex;         // slab functions of different slabs may fail on two threads at once
   mutable std::string error;
 };
 
@@ -423,33 +450,70 @@ int fail(tcb200_ctx* ctx, int code, const char* what, cudaError_t e = cudaSucces
 {
   std::string msg = what;
   if (e != cudaSuccess) { msg += ": "; msg += cudaGetErrorString(e); }
-  if (ctx) ctx->error = msg;
+  if (ctx) { std::lock_guard<std::mutex> lock(ctx->errorMutex); ctx->error = msg; }
   else { std::lock_guard<std::mutex> lock(g_errMutex); g_createError = msg; }
   return code;
 }
 
 #define TCB_CUDA(ctx, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, TCB200_E_CUDA, #call, e_); } while (0)
 
-typedef void (*KernelFn)(const uint8_t*, const uint16_t*, int, uint8_t*, int);
+typedef void (*KernelFn)(const uint8_t*, const uint16_t*, int, uint8_t*, int, const Variant, unsigned*);
 
-KernelFn select_kernel(int type, bool weightAlpha, int mode)
+template <bool V>
+KernelFn select_kernel_v(int type, bool weightAlpha, int mode)
 {
 #define TCB_PICK(T) \
   if (type == T) { \
-    if (mode == kRange) return encode_tiles_kernel<T, false, kRange>; \
-    if (mode == kCluster) return weightAlpha ? encode_tiles_kernel<T, true, kCluster> : encode_tiles_kernel<T, false, kCluster>; \
-    return weightAlpha ? encode_tiles_kernel<T, true, kIterative> : encode_tiles_kernel<T, false, kIterative>; \
+    if (mode == kRange) return encode_tiles_kernel<T, false, kRange, V>; \
+    if (mode == kCluster) return weightAlpha ? encode_tiles_kernel<T, true, kCluster, V> : encode_tiles_kernel<T, false, kCluster, V>; \
+    return weightAlpha ? encode_tiles_kernel<T, true, kIterative, V> : encode_tiles_kernel<T, false, kIterative, V>; \
   }
   TCB_PICK(1) TCB_PICK(2) TCB_PICK(3)
 #undef TCB_PICK
   return nullptr;
 }
 
+KernelFn select_kernel(int type, bool weightAlpha, int mode, bool general)
+{
+  return general ? select_kernel_v<true>(type, weightAlpha, mode) : select_kernel_v<false>(type, weightAlpha, mode);
+}
+
+// The host CPU's rcpps estimate as a table over the top `bits` mantissa bits of 1.m (what a libsquish built
+// with SQUISH_USE_SSE computes on this machine).  rcpps is a pure function of sign, exponent and those
+// bits on the CPUs seen so far (11 bits on Intel); the smallest width that reproduces a dense sample of
+// the instruction is chosen, and the claim is checked again by the tests against the instruction itself.
+uint32_t host_rcpps_bits(uint32_t xbits)
+{
+  float x; std::memcpy(&x, &xbits, 4);
+  const float y = _mm_cvtss_f32(_mm_rcp_ss(_mm_set_ss(x)));
+  uint32_t yb; std::memcpy(&yb, &y, 4);
+  return yb;
+}
+
+bool build_rcpps_table(std::vector<uint32_t>& table, int& bits)
+{
+  for (bits = 8; bits <= 14; ++bits) {
+    const int shift = 23 - bits;
+    table.assign((size_t)1 << bits, 0u);
+    bool ok = true;
+    for (uint32_t hi = 0; hi < (1u << bits) && ok; ++hi) {
+      const uint32_t first = host_rcpps_bits(0x3f800000u | (hi << shift));
+      table[hi] = first;
+      // every value of the remaining bits when there are few, else the ends plus a stride through them
+      const uint32_t span = 1u << shift, step = span > 512u ? span / 509u : 1u;
+      for (uint32_t lo = 1; lo < span && ok; lo += step) ok = host_rcpps_bits(0x3f800000u | (hi << shift) | lo) == first;
+      if (ok) ok = host_rcpps_bits(0x3f800000u | (hi << shift) | (span - 1u)) == first;
+    }
+    if (ok) return true;
+  }
+  return false;
+}
+
 int launch_encode(tcb200_ctx* ctx, const uint8_t* dTiles, const uint16_t* dWh, int n, uint8_t* dOut, cudaStream_t stream)
 {
   if (n <= 0) return TCB200_OK;
-  KernelFn fn = select_kernel(ctx->type, ctx->weightAlpha, ctx->mode);
-  fn<<<n, kThreads, ctx->smemBytes, stream>>>(dTiles, dWh, n, dOut, ctx->stride);
+  KernelFn fn = select_kernel(ctx->type, ctx->weightAlpha, ctx->mode, ctx->general);
+  fn<<<n, kThreads, ctx->smemBytes, stream>>>(dTiles, dWh, n, dOut, ctx->stride, ctx->variant, ctx->dBadTiles);
   ctx->launches.fetch_add(1);
   TCB_CUDA(ctx, cudaGetLastError());
   return TCB200_OK;
@@ -475,11 +539,32 @@ int tcb200_record_size(int type, int width, int height)
   return 0;
 }
 
+void tcb200_default_options(tcb200_options* opt)
+{
+  if (!opt) return;
+  opt->struct_size = (uint32_t)sizeof(tcb200_options);
+  opt->metric[0] = opt->metric[1] = opt->metric[2] = 1.0f;
+  opt->reciprocal = TCB200_RECIP_IEEE;
+}
+
 tcb200_ctx* tcb200_create(int device, int type, int quality, int max_batch_tiles)
+{
+  return tcb200_create_ex(device, type, quality, max_batch_tiles, nullptr);
+}
+
+tcb200_ctx* tcb200_create_ex(int device, int type, int quality, int max_batch_tiles, const tcb200_options* opt)
 {
   if (type < 1 || type > 3 || quality < 0 || quality > 9 || max_batch_tiles < 0) {
     fail(nullptr, TCB200_E_ARG, "tcb200_create: type must be 1..3, quality 0..9, max_batch_tiles >= 0");
     return nullptr;
+  }
+  if (opt) {
+    bool ok = opt->struct_size == sizeof(tcb200_options) && (opt->reciprocal == TCB200_RECIP_IEEE || opt->reciprocal == TCB200_RECIP_SSE);
+    for (int c = 0; ok && c < 3; ++c) ok = std::isfinite(opt->metric[c]) && opt->metric[c] >= 0.0f;
+    if (!ok) {
+      fail(nullptr, TCB200_E_ARG, "tcb200_create_ex: bad options (struct_size, metric must be finite and >= 0, reciprocal 0 or 1)");
+      return nullptr;
+    }
   }
   int count = tcb200_device_count();
   if (count <= 0 || device < 0 || device >= count) {
@@ -513,11 +598,40 @@ tcb200_ctx* tcb200_create(int device, int type, int quality, int max_batch_tiles
   static bool tablesOk = false;
   std::call_once(once, [] { tablesOk = build_tables(hostTables); });
   if (!tablesOk) { fail(nullptr, TCB200_E_ARG, "internal: candidate table overflow"); tcb200_destroy(ctx); return nullptr; }
-  if ((e = cudaMemcpyToSymbol(g_tables, &hostTables, sizeof(hostTables))) != cudaSuccess) return bail("cudaMemcpyToSymbol(g_tables)", e);
+  {
+    // one upload per device for the life of the process: other contexts' kernels may be reading g_tables
+    static std::mutex uploadMutex;
+    static bool uploaded[64] = {};
+    std::lock_guard<std::mutex> lock(uploadMutex);
+    if (device >= 64 || !uploaded[device]) {
+      if ((e = cudaMemcpyToSymbol(g_tables, &hostTables, sizeof(hostTables))) != cudaSuccess) return bail("cudaMemcpyToSymbol(g_tables)", e);
+      if (device < 64) uploaded[device] = true;
+    }
+  }
+  if ((e = cudaMalloc(&ctx->dBadTiles, sizeof(unsigned))) != cudaSuccess) return bail("cudaMalloc(status)", e);
+  if ((e = cudaMemset(ctx->dBadTiles, 0, sizeof(unsigned))) != cudaSuccess) return bail("cudaMemset(status)", e);
+  if (opt) {
+    ctx->variant.metric[0] = opt->metric[0]; ctx->variant.metric[1] = opt->metric[1]; ctx->variant.metric[2] = opt->metric[2];
+    ctx->variant.sse = opt->reciprocal == TCB200_RECIP_SSE ? 1 : 0;
+    ctx->general = ctx->variant.sse != 0 || opt->metric[0] != 1.0f || opt->metric[1] != 1.0f || opt->metric[2] != 1.0f;
+    if (ctx->variant.sse) {
+      std::vector<uint32_t> table;
+      int bits = 0;
+      if (!build_rcpps_table(table, bits)) {
+        fail(nullptr, TCB200_E_ARG, "tcb200_create_ex: this CPU's rcpps is not a function of <= 14 mantissa bits; TCB200_RECIP_SSE unsupported here");
+        tcb200_destroy(ctx);
+        return nullptr;
+      }
+      if ((e = cudaMalloc(&ctx->dRcp, table.size() * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc(rcpps table)", e);
+      if ((e = cudaMemcpy(ctx->dRcp, table.data(), table.size() * sizeof(uint32_t), cudaMemcpyHostToDevice)) != cudaSuccess) return bail("cudaMemcpy(rcpps table)", e);
+      ctx->variant.rcp = ctx->dRcp;
+      ctx->variant.rcpBits = bits;
+    }
+  }
 
   const size_t tileBytes = (type == 1) ? sizeof(TileShared<1>) : sizeof(TileShared<2>);
   ctx->smemBytes = tileBytes + sizeof(WarpJobs) * kWarps + (ctx->mode == kRange ? 0 : sizeof(WarpScratch) * kWarps);
-  KernelFn fn = select_kernel(ctx->type, ctx->weightAlpha, ctx->mode);
+  KernelFn fn = select_kernel(ctx->type, ctx->weightAlpha, ctx->mode, ctx->general);
   if ((e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smemBytes)) != cudaSuccess)
     return bail("cudaFuncSetAttribute(MaxDynamicSharedMemorySize)", e);
 
@@ -547,16 +661,62 @@ void tcb200_destroy(tcb200_ctx* ctx)
   }
   if (ctx->t0) cudaEventDestroy(ctx->t0);
   if (ctx->t1) cudaEventDestroy(ctx->t1);
+  cudaFree(ctx->dRcp);
+  cudaFree(ctx->dBadTiles);
   delete ctx;
 }
 
 const char* tcb200_last_error(const tcb200_ctx* ctx)
 {
-  if (ctx) return ctx->error.c_str();
-  std::lock_guard<std::mutex> lock(g_errMutex);
+  // a per-thread copy: the string a caller holds stays valid while another thread records a new error
   static thread_local std::string copy;
-  copy = g_createError;
+  if (ctx) { std::lock_guard<std::mutex> lock(ctx->errorMutex); copy = ctx->error; }
+  else { std::lock_guard<std::mutex> lock(g_errMutex); copy = g_createError; }
   return copy.c_str();
+}
+
+int tcb200_get_options(const tcb200_ctx* ctx, tcb200_options* opt)
+{
+  if (!ctx || !opt) return TCB200_E_ARG;
+  tcb200_default_options(opt);
+  opt->metric[0] = ctx->variant.metric[0]; opt->metric[1] = ctx->variant.metric[1]; opt->metric[2] = ctx->variant.metric[2];
+  opt->reciprocal = ctx->variant.sse ? TCB200_RECIP_SSE : TCB200_RECIP_IEEE;
+  return TCB200_OK;
+}
+
+long long tcb200_rejected_tiles(tcb200_ctx* ctx)
+{
+  if (!ctx) return (long long)TCB200_E_ARG;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return (long long)TCB200_E_CUDA;
+  unsigned bad = 0;
+  // cudaMemcpy orders itself after all prior work of the device's blocking streams only; the context's
+  // streams are non-blocking, so wait for them explicitly
+  for (int s = 0; s < kSlabs; ++s)
+    if (cudaStreamSynchronize(ctx->stream[s]) != cudaSuccess) { fail(ctx, TCB200_E_CUDA, "cudaStreamSynchronize", cudaGetLastError()); return (long long)TCB200_E_CUDA; }
+  if (cudaMemcpy(&bad, ctx->dBadTiles, sizeof(bad), cudaMemcpyDeviceToHost) != cudaSuccess) { fail(ctx, TCB200_E_CUDA, "cudaMemcpy(status)", cudaGetLastError()); return (long long)TCB200_E_CUDA; }
+  return (long long)bad;
+}
+
+int tcb200_selftest_rcpps(tcb200_ctx* ctx, const float* values, int n, float* estimates)
+{
+  if (!ctx) return TCB200_E_ARG;
+  if (n < 0 || (n > 0 && (!values || !estimates))) return fail(ctx, TCB200_E_ARG, "tcb200_selftest_rcpps: bad argument");
+  if (!ctx->variant.sse) return fail(ctx, TCB200_E_ARG, "tcb200_selftest_rcpps: context was not created with TCB200_RECIP_SSE");
+  if (n == 0) return TCB200_OK;
+  TCB_CUDA(ctx, cudaSetDevice(ctx->device));
+  float* d = nullptr;
+  TCB_CUDA(ctx, cudaMalloc(&d, (size_t)n * sizeof(float)));
+  cudaError_t e = cudaMemcpy(d, values, (size_t)n * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    rcpps_selftest_kernel<<<(n + 255) / 256, 256, 0, ctx->stream[0]>>>(d, n, ctx->variant);
+    ctx->launches.fetch_add(1);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream[0]);
+  if (e == cudaSuccess) e = cudaMemcpy(estimates, d, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(ctx, TCB200_E_CUDA, "tcb200_selftest_rcpps", e);
+  return TCB200_OK;
 }
 
 int tcb200_type(const tcb200_ctx* ctx) { return ctx ? ctx->type : 0; }
