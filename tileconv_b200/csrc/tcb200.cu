@@ -32,7 +32,7 @@ template <int TYPE> struct BlockWords { static constexpr int value = (TYPE == 1)
 // {w,h} is outside 1..64 (only reachable through tcb200_encode_device; the host entry points validate
 // before upload); such a tile gets a zero header and no blocks.
 template <int TYPE, bool WEIGHT_ALPHA, int MODE, bool VARIANT>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, TCB_MIN_CTAS)
 encode_tiles_kernel(const uint8_t* __restrict__ tiles, const uint16_t* __restrict__ wh, int ntiles,
                     uint8_t* __restrict__ out, int outStride, const Variant vp, unsigned* __restrict__ badTiles)
 {
@@ -139,7 +139,7 @@ encode_tiles_kernel(const uint8_t* __restrict__ tiles, const uint16_t* __restric
             construct_ordering(sc, lane, n, x, y, z, wgt, principle[0], principle[1], principle[2], 0);
             EarlySweep early;
             const uint32_t* cand4 = g_tables.cand + g_tables.off4[n];
-            early.r = run_sweep<4, VARIANT>(sc, lane, n, cand4, g_tables.cnt4[n], vp);
+            early.r = run_sweep<4, VARIANT>(sc, lane, n, cand4, g_tables.cnt4[n], vp, nullptr);
             early.entry = 0u;
             if (early.r.c != kNoCandidate) early.entry = sweep_endpoints<4, VARIANT>(sc, n, cand4, early.r.c, early.win, vp);
             cluster_fit<3, VARIANT>(sc, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, true, nullptr, best, vp);
@@ -462,20 +462,31 @@ typedef void (*KernelFn)(const uint8_t*, const uint16_t*, int, uint8_t*, int, co
 template <bool V>
 KernelFn select_kernel_v(int type, bool weightAlpha, int mode)
 {
+  // BC1 never weights by alpha (tcb200_create_ex clears the flag: alpha < 128 pixels leave the set)
+  if (type == 1)
+    return mode == kRange ? encode_tiles_kernel<1, false, kRange, V>
+         : mode == kCluster ? encode_tiles_kernel<1, false, kCluster, V> : encode_tiles_kernel<1, false, kIterative, V>;
 #define TCB_PICK(T) \
   if (type == T) { \
     if (mode == kRange) return encode_tiles_kernel<T, false, kRange, V>; \
     if (mode == kCluster) return weightAlpha ? encode_tiles_kernel<T, true, kCluster, V> : encode_tiles_kernel<T, false, kCluster, V>; \
     return weightAlpha ? encode_tiles_kernel<T, true, kIterative, V> : encode_tiles_kernel<T, false, kIterative, V>; \
   }
-  TCB_PICK(1) TCB_PICK(2) TCB_PICK(3)
+  TCB_PICK(2) TCB_PICK(3)
 #undef TCB_PICK
   return nullptr;
 }
 
 KernelFn select_kernel(int type, bool weightAlpha, int mode, bool general)
 {
+#if TCB_DEV_FEW_KERNELS   // tuning builds (tools/build_variants.sh): only what the sweeps time, for short compiles
+  if (general || type == 2) return nullptr;
+  if (type == 1) return mode == kRange ? encode_tiles_kernel<1, false, kRange, false>
+                      : mode == kCluster ? encode_tiles_kernel<1, false, kCluster, false> : encode_tiles_kernel<1, false, kIterative, false>;
+  return mode == kIterative && weightAlpha ? encode_tiles_kernel<3, true, kIterative, false> : nullptr;
+#else
   return general ? select_kernel_v<true>(type, weightAlpha, mode) : select_kernel_v<false>(type, weightAlpha, mode);
+#endif
 }
 
 // The host CPU's rcpps estimate as a table over the top `bits` mantissa bits of 1.m (what a libsquish built
@@ -632,6 +643,7 @@ tcb200_ctx* tcb200_create_ex(int device, int type, int quality, int max_batch_ti
   const size_t tileBytes = (type == 1) ? sizeof(TileShared<1>) : sizeof(TileShared<2>);
   ctx->smemBytes = tileBytes + sizeof(WarpJobs) * kWarps + (ctx->mode == kRange ? 0 : sizeof(WarpScratch) * kWarps);
   KernelFn fn = select_kernel(ctx->type, ctx->weightAlpha, ctx->mode, ctx->general);
+  if (!fn) { fail(nullptr, TCB200_E_ARG, "this build of libtcb200 does not contain the requested kernel"); tcb200_destroy(ctx); return nullptr; }
   if ((e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smemBytes)) != cudaSuccess)
     return bail("cudaFuncSetAttribute(MaxDynamicSharedMemorySize)", e);
 
