@@ -19,7 +19,15 @@ own `--batch` tiles per step).
   cpu_baseline the reference's own per-tile CPU path (oracle/_ref: reference glue + restated squish)
                on all host cores, bounded sample, rank 0 only.
 
+  modes        the metric's other modes (BC1 -q 2, BC3 -q 9, BC3 -q 2) on the same tiles: kernel-only AND
+               host-to-host through tcb200_encode(), each with its own roofline (ALU for the cluster levels,
+               measured pinned-copy bandwidth for the RangeFit levels, which are PCIe-bound end to end).
+  classes      kernel-only rate and ALU-roofline fraction per synthetic tile class (S-U, S-G, S-K).
+  e2e_in_process (N > 1) rank 0 re-runs the whole N-GPU job in ONE process through tcb200_encode_multi()
+               after the timed region and checks every shard against the ranks' own results.
+
 `--impl reference` times that CPU path alone (the reference arm).
+`--scaling strong --total T`: one T-tile job (BASELINE configs[4] literally: 1 M tiles) split N ways.
 """
 from __future__ import annotations
 
@@ -53,6 +61,9 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=65536, help="tiles per GPU per step")
     ap.add_argument("--cpu-sample", type=int, default=2048, help="tiles in the CPU baseline sample")
     ap.add_argument("--no-modes", action="store_true", help="skip the BC3/-q2 side measurements")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch tiles per GPU per step; strong: --total tiles per step split over the GPUs")
+    ap.add_argument("--total", type=int, default=1 << 20, help="tiles of the whole job per step with --scaling strong")
     return ap.parse_args()
 
 
@@ -129,9 +140,10 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
-def cpu_reference_rate(pool: np.ndarray, sample: int, type_: int, quality: int, repeats: int = 1):
-    """Times the reference's CPU path on all host cores over `sample` tiles.  Returns
-    (tiles_per_s, cores, kind, counters_per_tile)."""
+def cpu_reference_rate(pool: np.ndarray, sample: int, type_: int, quality: int, repeats: int = 3):
+    """Times the reference's CPU path on all host cores over `sample` tiles, best of `repeats` passes (the first
+    one warms the caches and the thread pool up).  Returns (tiles_per_s, cores, kind,
+    counters_per_tile)."""
     from oracle import pyoracle
     cores = os.cpu_count() or 1
     tiles = pool[:sample]
@@ -223,7 +235,7 @@ def run_reference(args, rank: int, world: int) -> int:
     rates = []
     kind, cores = "port", os.cpu_count() or 1
     for step in range(args.warmup + args.steps):
-        rate, cores, kind, _ = cpu_reference_rate(pool, sample, args.type, args.quality)
+        rate, cores, kind, _ = cpu_reference_rate(pool, sample, args.type, args.quality, repeats=1)
         if step >= args.warmup:
             rates.append(rate)
     value = len(rates) * sample / sum(sample / r for r in rates)
@@ -247,6 +259,53 @@ def run_reference(args, rank: int, world: int) -> int:
     return 0
 
 
+def oracle_counts(tiles: np.ndarray, type_: int, quality: int, threads: int) -> dict:
+    """Work the ORACLE does on `tiles` (instrumented counters of the restated squish), per tile."""
+    from oracle import pyoracle
+    pyoracle.totals_reset()
+    pyoracle.encode_tiles(tiles, type_, quality, threads)
+    c = pyoracle.totals()
+    return {k: v / len(tiles) for k, v in c.items()}
+
+
+def copy_peaks(torch, nbytes: int = 256 << 20) -> dict:
+    """Pinned-memory copy bandwidth of this GPU's host link, measured live with CUDA events: H2D alone, D2H alone and
+    both at once on two streams (GB/s each way).  The denominator of the PCIe roofline of the RangeFit levels."""
+    h_a = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    h_b = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    d_a = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    d_b = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def timed(fn, reps=4):
+        fn(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        s1.synchronize(); s2.synchronize()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e-3 / reps
+
+    def h2d():
+        with torch.cuda.stream(s1):
+            d_a.copy_(h_a, non_blocking=True)
+
+    def d2h():
+        with torch.cuda.stream(s2):
+            h_b.copy_(d_b, non_blocking=True)
+
+    def both():
+        h2d(); d2h()
+
+    # events recorded on the default stream bracket work on s1/s2 only through the explicit stream syncs above
+    t0 = time.perf_counter(); timed(h2d); t_h2d = timed(h2d)
+    t_d2h = timed(d2h); t_both = timed(both)
+    return {"h2d_gbs": nbytes / t_h2d / 1e9, "d2h_gbs": nbytes / t_d2h / 1e9,
+            "bidir_each_gbs": nbytes / t_both / 1e9, "bytes": nbytes,
+            "how": "torch pinned<->device copies of 256 MiB, wall time around 4 back-to-back copies bracketed by stream syncs"}
+
+
 def main() -> int:
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -258,7 +317,7 @@ def main() -> int:
 
     import torch
     import torch.distributed as dist
-    from tileconv_b200 import Encoder, capi
+    from tileconv_b200 import Encoder, capi, encode_multi, synth
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
@@ -266,36 +325,39 @@ def main() -> int:
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    # a host-side group for the one long wait (rank 0's in-process multi-GPU job): an NCCL barrier would park a
+    # spinning kernel on every waiting rank's GPU and time-slice it against rank 0's kernels on that GPU
+    cpu_group = dist.new_group(backend="gloo") if world > 1 else None
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def reduce_ranks(x: float, op) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+
     def max_over_ranks(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return reduce_ranks(x, dist.ReduceOp.MAX) if world > 1 else x
 
-    def sum_over_ranks(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
-    B = args.batch
+    strong = args.scaling == "strong"
+    total = args.total if strong else args.batch * world
+    first = total * rank // world                       # this rank's tile-index range [first, first + B)
+    B = total * (rank + 1) // world - first
     pool = make_pool()
     enc = Encoder(args.type, args.quality, device=local_rank, max_batch_tiles=8192)
     stride = enc.stride
+    cores = os.cpu_count() or 1
 
-    # ---- this rank's shard: global tiles [rank*B, (rank+1)*B) in pinned host memory ------------
+    # ---- this rank's shard in pinned host memory ------------------------------------------------
     h_in = capi.PinnedBuffer(B * capi.TILE_RECORD)
     h_out = capi.PinnedBuffer(B * stride)
     tiles = h_in.array.reshape(B, capi.TILE_RECORD)
-    fill_batch(tiles, pool, rank * B)
+    fill_batch(tiles, pool, first)
 
     d_in = torch.empty(B * capi.TILE_RECORD, dtype=torch.uint8, device="cuda")
     d_out = torch.zeros(B * stride, dtype=torch.uint8, device="cuda")
@@ -317,45 +379,60 @@ def main() -> int:
     launches = enc.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     ms_step = max_over_ranks(ms_kernel)
-    value = world * B / (ms_step * 1e-3)
+    value = total / (ms_step * 1e-3)
 
     # the device result of the timed run must be the real thing: spot-check it on rank 0 below
     dev_result = d_out.cpu().numpy().reshape(B, stride)
 
     # ---- end to end through the C ABI: pinned host in -> pinned host out -----------------------
-    for _ in range(min(args.warmup, 2)):
-        enc.encode_ptr(h_in.ptr, None, B, h_out.ptr)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        enc.encode_ptr(h_in.ptr, None, B, h_out.ptr)
-    torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / args.steps
-    e2e_s = max_over_ranks(e2e_s)
-    e2e_value = world * B / e2e_s
+    def time_e2e(e, out_ptr, steps, warm):
+        for _ in range(warm):
+            e.encode_ptr(h_in.ptr, None, B, out_ptr)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            e.encode_ptr(h_in.ptr, None, B, out_ptr)
+        torch.cuda.synchronize()
+        return max_over_ranks((time.perf_counter() - t0) / steps)
+
+    e2e_s = time_e2e(enc, h_out.ptr, args.steps, min(args.warmup, 2))
+    e2e_value = total / e2e_s
     host_result = h_out.array.reshape(B, stride)
     same = bool(np.array_equal(host_result, dev_result))
+    shard_sum = float(np.frombuffer(host_result.tobytes(), dtype=np.uint32).sum(dtype=np.uint64) % (1 << 52))
 
-    # ---- side measurements: the other modes the metric names (kernel only, fewer steps) ---------
+    # ---- live peaks (every rank measures its own GPU; rank 0's go into the line) ----------------
+    peak_fused = enc.fp32_peak(True) * 2.0      # FLOP/s, an FFMA counts 2
+    peak_unfused = enc.fp32_peak(False)         # FLOP/s of separate FMUL / FADD
+    barrier()
+    link = copy_peaks(torch) if not args.no_modes else None
+    barrier()
+
+    # ---- the metric's other modes on the same tiles: kernel only and host to host ---------------
     modes = {}
     if not args.no_modes:
-        for (t_, q_) in ((1, 2), (3, 9), (3, 2)):
+        for (t_, q_) in ((1, 9), (1, 2), (3, 9), (3, 2)):
             if (t_, q_) == (args.type, args.quality):
                 continue
-            with Encoder(t_, q_, device=local_rank, max_batch_tiles=1024) as e2:
+            with Encoder(t_, q_, device=local_rank, max_batch_tiles=8192) as e2:
                 d_o2 = torch.zeros(B * e2.stride, dtype=torch.uint8, device="cuda")
                 e2.encode_device(d_in.data_ptr(), None, B, d_o2.data_ptr())
                 torch.cuda.synchronize()
-                ms2 = e2.time_kernel_ms(d_in.data_ptr(), None, B, d_o2.data_ptr(), 2)
-                ms2 = max_over_ranks(ms2)
-                modes[f"bc{t_}_q{q_}"] = {"tiles_per_s": world * B / (ms2 * 1e-3), "ms_per_step": ms2}
+                ms2 = max_over_ranks(e2.time_kernel_ms(d_in.data_ptr(), None, B, d_o2.data_ptr(), 2))
                 del d_o2
+                h_o2 = capi.PinnedBuffer(B * e2.stride)
+                s2 = time_e2e(e2, h_o2.ptr, 3 if q_ <= 2 else 2, 1)
+                h_o2.free()
+                modes[f"bc{t_}_q{q_}"] = {"tiles_per_s": total / (ms2 * 1e-3), "ms_per_step": ms2,
+                                          "e2e": {"value": total / s2, "unit": "tiles/s", "ms_per_step": s2 * 1e3,
+                                                  "h2d_bytes_per_step": B * capi.TILE_RECORD, "d2h_bytes_per_step": B * e2.stride},
+                                          "_stride": e2.stride}
 
         # "next" row N3: the BCn decode kernel is the HBM-bound one of the set (2 KB in, 16 KB out per tile)
         for t_ in (1, 3):
             with Encoder(t_, 2, device=local_rank, max_batch_tiles=4096) as e3:
                 rec = torch.from_numpy(e3.encode(pool[:2048])).cuda()
-                reps_n = B // 2048
+                reps_n = max(1, min(B, 65536) // 2048)
                 d_rec = rec.repeat(reps_n, 1).contiguous()
                 d_pix = torch.empty(reps_n * 2048 * 4096 * 4, dtype=torch.uint8, device="cuda")
                 torch.cuda.synchronize()
@@ -367,26 +444,77 @@ def main() -> int:
                                            "roofline": {"bound": "hbm", "achieved": gbs, "unit": "GB/s", "bytes_per_tile": e3.stride + 16384}}
                 del d_rec, d_pix, rec
 
-    # ---- FP32 peaks measured live (rank 0's GPU) ------------------------------------------------
-    peak_fused = enc.fp32_peak(True) * 2.0      # FLOP/s, an FFMA counts 2
-    peak_unfused = enc.fp32_peak(False)         # FLOP/s of separate FMUL / FADD
+    # ---- kernel-only rate per synthetic tile class (rank 0's GPU; the bench mix is S-U + S-G) ----
+    classes = {}
+    class_pools = {}
+    if not args.no_modes and rank == 0:
+        nb = 16384
+        class_pools = {"S-U": synth.uniform_tiles(512, 1), "S-G": synth.smooth_tiles(512, 2), "S-K": synth.keyed_tiles(512, 3)}
+        d_o = torch.zeros(nb * stride, dtype=torch.uint8, device="cuda")
+        for name, cp in class_pools.items():
+            d_c = torch.from_numpy(np.concatenate([cp] * (nb // len(cp))).reshape(-1)).cuda()
+            torch.cuda.synchronize()
+            enc.encode_device(d_c.data_ptr(), None, nb, d_o.data_ptr())
+            msc = enc.time_kernel_ms(d_c.data_ptr(), None, nb, d_o.data_ptr(), 3)
+            classes[name] = {"tiles_per_s": nb / (msc * 1e-3), "tiles": nb}
+            del d_c
+        del d_o
+
+    if world > 1:
+        sums = [None] * world
+        dist.all_gather_object(sums, shard_sum)
+    else:
+        sums = [shard_sum]
 
     if rank != 0:
-        barrier()
+        torch.cuda.synchronize()
+        dist.barrier(group=cpu_group)      # rank 0 runs the in-process multi-GPU job meanwhile (GPU left idle)
         enc.close()
-        if world > 1:
-            dist.destroy_process_group()
+        dist.destroy_process_group()
         return 0
 
-    # ---- rank 0: CPU baseline, parity spot check, roofline --------------------------------------
+    # ---- rank 0: CPU baseline, parity spot check, rooflines --------------------------------------
     from oracle import pyoracle
     sample = min(args.cpu_sample, POOL_TILES)
     cpu_rate, cores, kind, per_tile = cpu_reference_rate(pool, sample, args.type, args.quality)
     shipped = as_shipped_cli_rate(pool, min(sample, 1024), args.type, args.quality)
     seam = pool_seam_rate(tiles[:min(B, 65536)], args.type, args.quality) if world == 1 else None
-    # parity of the measured outputs: the first `sample` tiles of the batch are pool tiles (copy 0)
+    # parity of the measured outputs: rank 0's first tiles are pool tiles (copy 0)
     want = pyoracle.encode_tiles(pool[:256], args.type, args.quality, threads=cores)
-    parity_ok = bool(np.array_equal(dev_result[:256], want)) if rank * B == 0 else None
+    parity_ok = bool(np.array_equal(dev_result[:256], want))
+
+    # ---- N > 1: the same N-GPU job in ONE process through tcb200_encode_multi --------------------
+    in_process = None
+    if world > 1:
+        try:
+            encs = [enc] + [Encoder(args.type, args.quality, device=g, max_batch_tiles=8192) for g in range(1, world)]
+            m_in = capi.PinnedBuffer(total * capi.TILE_RECORD)
+            m_out = capi.PinnedBuffer(total * stride)
+            mt = m_in.array.reshape(total, capi.TILE_RECORD)
+            for g in range(world):
+                lo, hi = total * g // world, total * (g + 1) // world
+                fill_batch(mt[lo:hi], pool, lo)
+            encode_multi(encs, m_in.ptr, None, total, m_out.ptr)          # warm-up (contexts, first touch)
+            t0 = time.perf_counter()
+            reps = 2
+            for _ in range(reps):
+                encode_multi(encs, m_in.ptr, None, total, m_out.ptr)
+            dt = (time.perf_counter() - t0) / reps
+            mo = m_out.array.reshape(total, stride)
+            ok = []
+            for g in range(world):
+                lo, hi = total * g // world, total * (g + 1) // world
+                sg = float(np.frombuffer(mo[lo:hi].tobytes(), dtype=np.uint32).sum(dtype=np.uint64) % (1 << 52))
+                ok.append(sg == sums[g])
+            in_process = {"value": total / dt, "unit": "tiles/s", "n_gpus": world, "ms_per_step": dt * 1e3,
+                          "path": "tcb200_encode_multi(): one process, one host thread + 3 streams per device, D2H into disjoint slices of one pinned buffer",
+                          "shards_match_rank_results": bool(all(ok)), "vs_torchrun_e2e": (total / dt) / e2e_value}
+            for e in encs[1:]:
+                e.close()
+            m_in.free(); m_out.free()
+        except Exception as exc:   # reported, never hidden
+            in_process = {"error": str(exc)}
+        dist.barrier(group=cpu_group)
 
     flops_tile = flops_per_tile(per_tile)
     achieved_tflops = flops_tile * (B / (ms_kernel * 1e-3)) / 1e12          # this rank's kernel
@@ -399,57 +527,87 @@ def main() -> int:
     except Exception:
         pass
 
-    for m in modes.values():
-        if "roofline" in m:
+    def alu_roofline(rate_per_gpu: float, counts: dict) -> dict:
+        ft = flops_per_tile(counts)
+        tf = ft * rate_per_gpu / 1e12
+        return {"bound": "fp32_alu", "achieved": tf, "peak": peak_fused / 1e12, "unit": "TFLOP/s", "frac": tf / (peak_fused / 1e12),
+                "peak_unfused": peak_unfused / 1e12, "frac_of_unfused": tf / (peak_unfused / 1e12), "flops_per_tile": ft,
+                "candidates_per_tile": {"c3": counts["cand3"], "c4": counts["cand4"]}}
+
+    for name, m in modes.items():
+        if "roofline" in m:          # decode kernels: HBM
             m["roofline"].update({"peak": hbm_peak, "frac": m["roofline"]["achieved"] / hbm_peak, "peak_source": f"MEASURED_PEAKS.json ({hbm_src})"})
+            continue
+        t_, q_ = int(name[2]), int(name[-1])
+        st = m.pop("_stride")
+        per_gpu_e2e = m["e2e"]["value"] / world
+        if q_ <= 2:
+            # RangeFit levels: the kernel needs ~3 % of HBM bandwidth and host to host the link is the limit
+            h2d = per_gpu_e2e * capi.TILE_RECORD / 1e9
+            d2h = per_gpu_e2e * st / 1e9
+            m["roofline"] = {"bound": "pcie_h2d", "achieved": h2d, "peak": link["h2d_gbs"], "unit": "GB/s", "frac": h2d / link["h2d_gbs"],
+                             "d2h_achieved": d2h, "d2h_peak_while_h2d_runs": link["bidir_each_gbs"],
+                             "limiter": "host->device copy of the 5120-byte tile records over the GPU's host link (kernel-only rate is "
+                                        f"{m['tiles_per_s'] / world / 1e6:.1f} M tiles/s per GPU)",
+                             "peak_source": "pinned-copy bandwidth measured live (link)"}
+            m["kernel_hbm"] = {"bound": "hbm", "achieved": (capi.TILE_RECORD + st) * m["tiles_per_s"] / world / 1e9, "peak": hbm_peak, "unit": "GB/s"}
+            m["kernel_hbm"]["frac"] = m["kernel_hbm"]["achieved"] / hbm_peak
+        else:
+            m["roofline"] = alu_roofline(m["tiles_per_s"] / world, oracle_counts(pool[:256], t_, q_, cores))
+    for name, c in classes.items():
+        c["roofline"] = alu_roofline(c["tiles_per_s"], oracle_counts(class_pools[name][:64], args.type, args.quality, cores))
 
     traffic, ncu_facts = None, None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-            t = json.load(f).get(f"bc{args.type}_q{args.quality}_batch{B}")
-        if t:
-            traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
-            ncu_facts = {k: t[k] for k in ("smsp_issue_active_pct", "sm_pipe_fma_cycles_active_pct", "active_lanes_per_instruction",
-                                           "dominant_stall") if k in t}
-    except Exception:
-        pass
+    for prof in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", prof)) as f:
+                t = json.load(f).get(f"bc{args.type}_q{args.quality}_batch{B}")
+            if t:
+                traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
+                ncu_facts = {k: t[k] for k in ("smsp_issue_active_pct", "sm_pipe_fma_cycles_active_pct", "active_lanes_per_instruction",
+                                               "dominant_stall") if k in t}
+                ncu_facts["source"] = "profiles/" + prof
+                break
+        except Exception:
+            pass
+
+    main_roof = alu_roofline(B / (ms_kernel * 1e-3), per_tile)
+    main_roof.update({"traffic": traffic,
+                      "traffic_note": "DRAM bytes of one launch from the committed ncu capture (profiles/); algorithmic bytes per launch = " + str(bytes_tile * B),
+                      "peak_source": "FFMA loop measured live by tcb200_fp32_peak (an FFMA = 2 flops)",
+                      "note": "bit-exactness forbids mul+add fusion, so the attainable ceiling is peak_unfused (separate FMUL/FADD)",
+                      "ncu": ncu_facts,      # from the committed capture of this configuration, not measured in this run
+                      "classes": {k: {"tiles_per_s": v["tiles_per_s"], "frac": v["roofline"]["frac"], "frac_of_unfused": v["roofline"]["frac_of_unfused"],
+                                      "achieved": v["roofline"]["achieved"]} for k, v in classes.items()},
+                      "hbm": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
+                              "bytes_per_tile": bytes_tile, "peak_source": f"MEASURED_PEAKS.json ({hbm_src})"}})
 
     line = {
         "metric": f"tiles_per_s_bc{args.type}_q{args.quality}", "value": value, "unit": "tiles/s",
         "mpix_per_s": value * 4096 / 1e6,
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.type, args.quality, B),
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.type, args.quality, B) + (f" (strong scaling: one {total}-tile job)" if strong else ""),
                    "l2": f"inputs larger than L2: {B * capi.TILE_RECORD / 1e6:.0f} MB read per step per GPU",
                    "timing": "CUDA events on the launching stream around K back-to-back launches, max over ranks"},
         "e2e": {"value": e2e_value, "unit": "tiles/s", "h2d_bytes_per_step": B * capi.TILE_RECORD, "d2h_bytes_per_step": B * stride,
                 "ms_per_step": e2e_s * 1e3, "path": "tcb200_encode(): pinned host -> H2D -> kernel -> D2H -> pinned host, 8192-tile chunks on 3 streams",
                 "matches_device_result": same},
+        "e2e_in_process": in_process,
         "gpu_launches": int(launches),
         "wall_ms_per_step": 1e3 * t_wall / args.steps,
         "clocks": clocks,
-        "roofline": {"bound": "fp32_alu", "achieved": achieved_tflops, "peak": peak_fused / 1e12, "unit": "TFLOP/s",
-                     "frac": achieved_tflops / (peak_fused / 1e12), "traffic": traffic,
-                     "traffic_note": "DRAM bytes of one launch from the ncu capture in profiles/r1_traffic.json; algorithmic bytes per launch = "
-                                     + str(bytes_tile * B),
-                     "peak_source": "FFMA loop measured live by tcb200_fp32_peak (an FFMA = 2 flops)",
-                     "peak_unfused": peak_unfused / 1e12,
-                     "frac_of_unfused": achieved_tflops / (peak_unfused / 1e12),
-                     "note": "bit-exactness forbids mul+add fusion, so the attainable ceiling is peak_unfused (separate FMUL/FADD)",
-                     "ncu": ncu_facts,      # from the committed capture of this configuration (profiles/), not measured in this run
-                     "flops_per_tile": flops_tile,
-                     "candidates_per_tile": {"c3": per_tile["cand3"], "c4": per_tile["cand4"]},
-                     "hbm": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
-                             "bytes_per_tile": bytes_tile, "peak_source": f"MEASURED_PEAKS.json ({hbm_src})"}},
+        "roofline": main_roof,
         "cpu_baseline": {"value": cpu_rate, "unit": "tiles/s", "cores": cores, "kind": kind,
-                         "sample": f"{sample} pool tiles, {cores} threads over the reference's TileData::encode (-u), restated squish",
+                         "sample": f"{sample} pool tiles, {cores} threads over the reference's TileData::encode (-u), restated squish, best of 3 passes",
                          "as_shipped_cli": shipped},
         "e2e_pool_seam": seam,
         "parity_spot_check": parity_ok,
+        "link": link,
         "modes": modes,
+        "classes": classes,
     }
     print(json.dumps(line), flush=True)
-    barrier()
     enc.close()
     if world > 1:
         dist.destroy_process_group()

@@ -104,6 +104,17 @@ int tcb200_record_stride(const tcb200_ctx* ctx);   /* = tcb200_record_size(type,
  * (tileconv/converter.h:85) as driven by TileData::encode (tileconv/tiledata.cpp:111-162, -u path). */
 int tcb200_encode(tcb200_ctx* ctx, const uint8_t* tiles, const uint16_t* wh, int n, uint8_t* out);
 
+/* Multi-GPU form of tcb200_encode, the in-process replacement of the reference's fan-out object
+ * (createThreadPool + TileThreadPool, tileconv/tilethreadpool_base.h:38-81, tilethreadpool_posix.cpp:33-36):
+ * ctxs[0..n_ctx) are contexts on DIFFERENT devices created with the same type, quality and options.  The tile
+ * index range is cut into n_ctx contiguous shards, [g*n/n_ctx, (g+1)*n/n_ctx) goes to ctxs[g]; every device
+ * uploads, encodes and downloads its shard on its own streams (one host thread per context inside the call)
+ * and writes its records straight into out + first_tile*stride.  No collective, no reordering: records have a
+ * fixed stride and tiles are independent.  Returns when `out` is complete; the first failing
+ * shard's code, message via tcb200_last_error(ctxs[0]).  Pinned host buffers (tcb200_host_alloc) are needed
+ * for the copies to overlap the kernels. */
+int tcb200_encode_multi(tcb200_ctx* const* ctxs, int n_ctx, const uint8_t* tiles, const uint16_t* wh, int n, uint8_t* out);
+
 /* Device-resident variant: all three pointers are device pointers on ctx's device; the kernel is
  * enqueued on `stream` (a cudaStream_t passed as void*, NULL = the context's compute stream) and
  * the call returns without synchronising.  d_tiles must be 16-byte aligned (the kernel stages records

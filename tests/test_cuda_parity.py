@@ -367,3 +367,43 @@ def test_encode_device_rejects_bad_tile_sizes(oracle):
                 assert (out[i, :4] == 0).all() and (out[i, 4:] == 0xAB).all()
             enc.encode_device(d_in.data_ptr(), None, 6, d_out.data_ptr())
             assert enc.rejected_tiles() == 3
+
+
+# ---- tcb200_encode_multi: the in-process multi-GPU entry point -------------------------------------------
+def test_encode_multi_shards_match_single_context(oracle):
+    """Contiguous tile-range shards over several contexts == one context, for an uneven split and ragged tiles.
+    On a one-GPU box the contexts share device 0 (the sharding and the disjoint output slices are the same
+    code); with more devices visible each context sits on its own GPU."""
+    from tileconv_b200 import capi, device_count, encode_multi
+    ndev = device_count()
+    tiles, wh = synth.ragged_tiles(1001, 171)
+    wh = np.ascontiguousarray(wh, np.uint16)
+    for type_, quality, nctx in ((1, 9, 3), (3, 2, 2), (2, 4, max(2, min(ndev, 8)))):
+        encs = [encoder(type_, quality, device=g % ndev, max_batch_tiles=128) for g in range(nctx)]
+        try:
+            want = encs[0].encode(tiles, wh)
+            out = np.zeros_like(want)
+            encode_multi(encs, tiles.ctypes.data, wh.ctypes.data, len(tiles), out.ctypes.data)
+            for i in range(len(tiles)):
+                size = oracle.record_size(type_, int(wh[i, 0]), int(wh[i, 1]))
+                assert np.array_equal(out[i, :size], want[i, :size]), (type_, quality, i)
+            # n smaller than the number of contexts, and n = 0
+            out2 = np.zeros((1, encs[0].stride), np.uint8)
+            encode_multi(encs, tiles.ctypes.data, None, 1, out2.ctypes.data)
+            assert np.array_equal(out2, encs[0].encode(tiles[:1]))
+            encode_multi(encs, None, None, 0, None)
+        finally:
+            for e in encs:
+                e.close()
+
+
+def test_encode_multi_rejects_mismatched_contexts():
+    from tileconv_b200 import TcbError, encode_multi
+    tiles = synth.uniform_tiles(4, 181)
+    out = np.zeros((4, 2052), np.uint8)
+    with encoder(1, 9) as a, encoder(1, 4) as b, encoder(1, 9, metric=(0.5, 1.0, 1.0)) as c:
+        for bad in ([a, b], [a, c], [a, a]):
+            with pytest.raises(TcbError):
+                encode_multi(bad, tiles.ctypes.data, None, 4, out.ctypes.data)
+        with pytest.raises(TcbError):       # bad sizes are caught by the shard's own validation
+            encode_multi([a], tiles.ctypes.data, np.array([[0, 1]] * 4, np.uint16).ctypes.data, 4, out.ctypes.data)

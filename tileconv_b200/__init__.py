@@ -10,9 +10,10 @@ from .capi import (  # noqa: F401
     Encoder,
     TcbError,
     device_count,
+    encode_multi,
     library_path,
     load_library,
     record_size,
 )
 
-__all__ = ["Encoder", "TcbError", "device_count", "library_path", "load_library", "record_size"]
+__all__ = ["Encoder", "TcbError", "device_count", "encode_multi", "library_path", "load_library", "record_size"]

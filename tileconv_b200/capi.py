@@ -41,6 +41,7 @@ SYMBOLS = [
     ("tcb200_device", ctypes.c_int, [ctypes.c_void_p]),
     ("tcb200_record_stride", ctypes.c_int, [ctypes.c_void_p]),
     ("tcb200_encode", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+    ("tcb200_encode_multi", ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     ("tcb200_encode_device", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     ("tcb200_slab_count", ctypes.c_int, [ctypes.c_void_p]),
     ("tcb200_slab_capacity", ctypes.c_int, [ctypes.c_void_p]),
@@ -124,6 +125,16 @@ class PinnedBuffer:
             self.free()
         except Exception:
             pass
+
+
+def encode_multi(encoders, tiles_ptr: int, wh_ptr: Optional[int], n: int, out_ptr: int) -> None:
+    """tcb200_encode_multi over the contexts of `encoders` (one per device): host pointers in, host pointers out."""
+    lib = load_library()
+    arr = (ctypes.c_void_p * len(encoders))(*[e.handle for e in encoders])
+    rc = lib.tcb200_encode_multi(arr, len(encoders), tiles_ptr, wh_ptr, n, out_ptr)
+    if rc != 0:
+        msg = lib.tcb200_last_error(encoders[0].handle) if encoders and encoders[0].handle else b""
+        raise TcbError(f"tcb200_encode_multi failed ({rc}): {(msg or b'').decode()}")
 
 
 class Encoder:

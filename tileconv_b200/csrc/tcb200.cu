@@ -14,6 +14,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 #include <xmmintrin.h>
 
@@ -773,6 +774,45 @@ int tcb200_encode(tcb200_ctx* ctx, const uint8_t* tiles, const uint16_t* wh, int
     TCB_CUDA(ctx, cudaMemcpyAsync(out + (size_t)first * ctx->stride, ctx->dOut[s], (size_t)m * ctx->stride, cudaMemcpyDeviceToHost, st));
   }
   for (int s = 0; s < kSlabs; ++s) TCB_CUDA(ctx, cudaStreamSynchronize(ctx->stream[s]));
+  return TCB200_OK;
+}
+
+int tcb200_encode_multi(tcb200_ctx* const* ctxs, int n_ctx, const uint8_t* tiles, const uint16_t* wh, int n, uint8_t* out)
+{
+  if (!ctxs || n_ctx < 1 || !ctxs[0]) return TCB200_E_ARG;
+  tcb200_ctx* first = ctxs[0];
+  if (n < 0 || (n > 0 && (!tiles || !out))) return fail(first, TCB200_E_ARG, "tcb200_encode_multi: bad argument");
+  for (int g = 1; g < n_ctx; ++g) {
+    if (!ctxs[g]) return fail(first, TCB200_E_ARG, "tcb200_encode_multi: null context");
+    const tcb200_ctx* c = ctxs[g];
+    if (c->type != first->type || c->quality != first->quality || c->general != first->general || c->variant.sse != first->variant.sse ||
+        c->variant.metric[0] != first->variant.metric[0] || c->variant.metric[1] != first->variant.metric[1] || c->variant.metric[2] != first->variant.metric[2])
+      return fail(first, TCB200_E_ARG, "tcb200_encode_multi: contexts differ in type, quality or options");
+    for (int h = 0; h < g; ++h)
+      if (ctxs[h] == c) return fail(first, TCB200_E_ARG, "tcb200_encode_multi: the same context appears twice");
+  }
+  // shard g = tiles [g*n/G, (g+1)*n/G): contiguous ranges, fixed-stride records => every device writes its own
+  // slice of `out`, nothing to gather or reorder.  One host thread drives each context.
+  std::vector<int> rc((size_t)n_ctx, TCB200_OK);
+  auto shard = [&](int g) {
+    const long long lo = (long long)n * g / n_ctx, hi = (long long)n * (g + 1) / n_ctx;
+    rc[(size_t)g] = tcb200_encode(ctxs[g], tiles + (size_t)lo * kTileRecord, wh ? wh + (size_t)lo * 2 : nullptr, (int)(hi - lo),
+                                  out + (size_t)lo * first->stride);
+  };
+  std::vector<std::thread> workers;
+  try {
+    for (int g = 1; g < n_ctx; ++g) workers.emplace_back(shard, g);
+  } catch (...) {
+    for (auto& w : workers) w.join();
+    return fail(first, TCB200_E_NOMEM, "tcb200_encode_multi: could not start a host thread");
+  }
+  shard(0);
+  for (auto& w : workers) w.join();
+  for (int g = 0; g < n_ctx; ++g)
+    if (rc[(size_t)g] != TCB200_OK) {
+      if (g != 0) fail(first, rc[(size_t)g], (std::string("tcb200_encode_multi: device ") + std::to_string(ctxs[g]->device) + ": " + tcb200_last_error(ctxs[g])).c_str());
+      return rc[(size_t)g];
+    }
   return TCB200_OK;
 }
 
