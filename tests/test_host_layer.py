@@ -294,3 +294,48 @@ def test_reference_cli_with_plugin_writes_identical_files(tmp_path, args):
     res = subprocess.run([TBC_ENCODE, "-s", "-o", dst] + args + [src], capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stderr
     assert open(dst, "rb").read() == outs[0]
+
+
+# ---- the streaming fast path (slab_pipeline) vs the TileData route --------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("type_,quality,deflate", ((1, 9, 0), (1, 2, 1), (3, 6, 0), (2, 4, 1)))
+def test_slab_pipeline_and_tiledata_route_write_the_same_files(host, tmp_path, monkeypatch, type_, quality, deflate):
+    """tbc_encode streams tile records through the pinned slabs; TCB200_TILEDATA_ROUTE=1 selects the reference-style
+    caller loop (one TileData per tile through createThreadPool).  Same bytes, for a TIS with several slabs per
+    device (small slabs forced), a one-tile TIS and a MOS with ragged edge tiles."""
+    tiles = np.concatenate([synth.mixed_tiles(700, 191), synth.keyed_tiles(333, 192)])
+    cases = []
+    src = str(tmp_path / "big.tis"); write_tis(src, tiles, header=True); cases.append((src, 0))
+    src = str(tmp_path / "one.tis"); write_tis(src, tiles[:1], header=False); cases.append((src, 1))
+    src = str(tmp_path / "edge.mos"); open(src, "wb").write(make_mos(333, 197, 193)[0]); cases.append((src, 0))
+    for src, assume in cases:
+        outs = []
+        for route, slab in (("0", "97"), ("1", "")):
+            monkeypatch.setenv("TCB200_TILEDATA_ROUTE", route)
+            if slab:
+                monkeypatch.setenv("TCB200_SLAB_TILES", slab)
+            else:
+                monkeypatch.delenv("TCB200_SLAB_TILES", raising=False)
+            dst = src + ".out" + route
+            assert host.tcbh_encode_file(src.encode(), dst.encode(), type_, quality, deflate, assume, 3) == 0, host.tcbh_last_error()
+            outs.append(open(dst, "rb").read())
+        assert outs[0] == outs[1], src
+    monkeypatch.delenv("TCB200_TILEDATA_ROUTE", raising=False)
+    monkeypatch.delenv("TCB200_SLAB_TILES", raising=False)
+
+
+@pytest.mark.gpu
+def test_slab_pipeline_failures_leave_no_output(host, tmp_path):
+    src, dst = str(tmp_path / "short.tis"), str(tmp_path / "short.tbc")
+    with open(src, "wb") as f:
+        f.write(b"TIS V1  " + struct.pack("<IIII", 10, 0x1400, 0x18, 0x40) + bytes(5120 * 3))     # claims 10 tiles, holds 3
+    assert host.tcbh_encode_file(src.encode(), dst.encode(), 1, 2, 0, 0, 2) != 0
+    assert b"Incomplete" in host.tcbh_last_error() and not os.path.exists(dst)
+    # a MOS whose offset table points outside the file
+    mos = bytearray(make_mos(100, 64, 194)[0])
+    table = 24 + 2 * 1024
+    mos[table + 4:table + 8] = struct.pack("<I", 1 << 30)
+    src, dst = str(tmp_path / "bad.mos"), str(tmp_path / "bad.mbc")
+    open(src, "wb").write(bytes(mos))
+    assert host.tcbh_encode_file(src.encode(), dst.encode(), 1, 2, 0, 0, 2) != 0
+    assert not os.path.exists(dst)

@@ -1,4 +1,9 @@
 #include "tile_stream.h"
+#include "slab_pipeline.h"
+
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -84,6 +89,103 @@ bool pumpTiles(const Options& options, unsigned count, Provider provider, std::F
   return true;
 }
 
+// ---- fast path (slab_pipeline.h): file descriptors instead of per-tile objects ------------------------------
+struct Fd
+{
+  int fd;
+  explicit Fd(int f) : fd(f) {}
+  ~Fd() { if (fd >= 0) ::close(fd); }
+};
+
+bool preadAll(int fd, uint8_t* p, size_t n, unsigned long long off)
+{
+  while (n > 0) {
+    const ssize_t r = ::pread(fd, p, n, (off_t)off);
+    if (r <= 0) return false;
+    p += r; n -= (size_t)r; off += (unsigned long long)r;
+  }
+  return true;
+}
+
+// A TIS body is count x 5120 bytes, i.e. already an array of tile records.
+class TisFeed : public TileFeed
+{
+public:
+  TisFeed(int fd, unsigned long long bodyOffset, unsigned count) : m_fd(fd), m_body(bodyOffset), m_count(count) {}
+  unsigned count() const noexcept override { return m_count; }
+  bool fill(unsigned first, unsigned n, uint8_t* records, uint16_t* wh) noexcept override
+  {
+    for (unsigned i = 0; i < 2 * n; ++i) wh[i] = 64;
+    return preadAll(m_fd, records, (size_t)n * 5120, m_body + (unsigned long long)first * 5120);
+  }
+private:
+  int m_fd;
+  unsigned long long m_body;
+  unsigned m_count;
+};
+
+// MOS: palettes, offset table and pixel data are separate arrays; edge tiles are narrower than 64
+// (tileconv/graphics.cpp:296-297, 322-342).
+class MosFeed : public TileFeed
+{
+public:
+  MosFeed(const std::vector<uint8_t>& mos, unsigned width, unsigned height, uint32_t palOfs)
+  : m_mos(mos), m_width(width), m_height(height), m_cols((width + 63) >> 6), m_rows((height + 63) >> 6), m_palOfs(palOfs)
+  {
+    m_tableOfs = (size_t)palOfs + (size_t)count() * PALETTE_SIZE;
+    m_dataOfs = m_tableOfs + (size_t)count() * 4;
+  }
+  unsigned count() const noexcept override { return m_cols * m_rows; }
+  void dims(unsigned i, uint16_t& w, uint16_t& h) const noexcept override
+  {
+    const unsigned row = i / m_cols, col = i % m_cols;
+    w = (uint16_t)std::min(64u, m_width - col * 64); h = (uint16_t)std::min(64u, m_height - row * 64);
+  }
+  bool fill(unsigned first, unsigned n, uint8_t* records, uint16_t* wh) noexcept override
+  {
+    for (unsigned k = 0; k < n; ++k) {
+      const unsigned i = first + k, row = i / m_cols, col = i % m_cols;
+      const unsigned w = std::min(64u, m_width - col * 64), h = std::min(64u, m_height - row * 64);
+      const size_t ofs = m_dataOfs + rd32(m_mos.data() + m_tableOfs + (size_t)i * 4);
+      if (ofs + (size_t)w * h > m_mos.size()) return false;
+      uint8_t* rec = records + (size_t)k * 5120;
+      std::memcpy(rec, m_mos.data() + m_palOfs + (size_t)i * PALETTE_SIZE, PALETTE_SIZE);
+      std::memcpy(rec + PALETTE_SIZE, m_mos.data() + ofs, (size_t)w * h);
+      wh[2 * k] = (uint16_t)w; wh[2 * k + 1] = (uint16_t)h;
+    }
+    return true;
+  }
+private:
+  const std::vector<uint8_t>& m_mos;
+  unsigned m_width, m_height, m_cols, m_rows;
+  uint32_t m_palOfs;
+  size_t m_tableOfs, m_dataOfs;
+};
+
+void reportTimes(const PipelineTimes& t)
+{
+  if (!std::getenv("TCB200_TIMING")) return;
+  std::fprintf(stderr, "{\"tiles\": %llu, \"devices\": %d, \"slab_tiles\": %d, \"threads\": %d, \"setup_s\": %.4f, \"total_s\": %.4f, "
+               "\"tiles_per_s\": %.1f, \"fill_s\": %.4f, \"submit_s\": %.4f, \"gpu_wait_s\": %.4f, \"frame_s\": %.4f, \"write_s\": %.4f, "
+               "\"bytes_in\": %llu, \"bytes_out\": %llu}\n",
+               t.tiles, t.devices, t.slabTiles, t.threads, t.setup, t.total, t.total > 0 ? (double)t.tiles / t.total : 0.0,
+               t.fill, t.submit, t.gpuWait, t.frame, t.write, t.bytesIn, t.bytesOut);
+}
+
+// header + framed tiles through the slab pipeline; removes the partial output on failure (graphics.cpp:77,161)
+bool encodeFast(const Options& options, TileFeed& feed, const std::string& outFile, const uint8_t* header, size_t headerSize, std::string& error)
+{
+  Fd out(::open(outFile.c_str(), O_RDWR | O_CREAT | O_TRUNC, 0644));
+  if (out.fd < 0) { error = "Error opening output file"; return false; }
+  bool ok = ::pwrite(out.fd, header, headerSize, 0) == (ssize_t)headerSize;
+  if (!ok) error = "Error while writing header";
+  PipelineTimes times;
+  if (ok) ok = runSlabPipeline(options, feed, out.fd, headerSize, error, &times);
+  if (!ok) { ::unlink(outFile.c_str()); return false; }
+  reportTimes(times);
+  return true;
+}
+
 struct OutputFile
 {
   std::string path;
@@ -111,8 +213,43 @@ InputKind sniffInput(const std::string& path, bool assumeTis) noexcept
 
 bool encodeTisFile(const Options& options, const std::string& inFile, const std::string& outFile, std::string& error) noexcept
 {
+  if (inFile.empty() || outFile.empty() || inFile == outFile) { error = "Error opening input file"; return false; }
+  if (slabPipelineApplies(options)) {
+    // same checks as below, on the header alone; the body is streamed straight into the pinned slabs
+    Fd in(::open(inFile.c_str(), O_RDONLY));
+    struct stat st;
+    if (in.fd < 0 || ::fstat(in.fd, &st) != 0) { error = "Error opening input file"; return false; }
+    const unsigned long long size = (unsigned long long)st.st_size;
+    uint8_t h[24] = { 0 };
+    if (size >= 4 && !preadAll(in.fd, h, (size_t)std::min<unsigned long long>(24, size), 0)) { error = "Error opening input file"; return false; }
+    unsigned long long first = 0;
+    uint32_t count = 0;
+    if (size >= 4 && std::memcmp(h, "TIS ", 4) == 0) {
+      if (size < 24) { error = "Invalid TIS header"; return false; }
+      if (std::memcmp(h + 4, "V1  ", 4) != 0 && std::memcmp(h + 4, "V2  ", 4) != 0) { error = "Invalid TIS version"; return false; }
+      count = rd32(h + 8);
+      if (count == 0) { error = "No tiles found"; return false; }
+      if (rd32(h + 12) != 0x1400) { error = "Invalid tile size"; return false; }
+      if (rd32(h + 16) < 0x18) { error = "Invalid header size"; return false; }
+      if (rd32(h + 20) != 0x40) { error = "Invalid tile dimensions"; return false; }
+      first = 24;
+    } else if (options.assumeTis()) {
+      if (size == 0 || size % 5120 != 0) { error = "Headerless TIS has wrong file size"; return false; }
+      count = (uint32_t)(size / 5120);
+    } else {
+      error = "Invalid TIS signature";
+      return false;
+    }
+    if (size < first + (unsigned long long)count * 5120) { error = "Incomplete TIS file"; return false; }
+    uint8_t header[HEADER_TBC_SIZE];
+    std::memcpy(header, "TBC V1.0", 8);
+    wr32(header + 8, Options::GetEncodingCode(options.getEncoding(), options.isDeflate()));
+    wr32(header + 12, count);
+    TisFeed feed(in.fd, first, count);
+    return encodeFast(options, feed, outFile, header, sizeof(header), error);
+  }
   std::vector<uint8_t> data;
-  if (inFile.empty() || outFile.empty() || inFile == outFile || !readAll(inFile, data)) { error = "Error opening input file"; return false; }
+  if (!readAll(inFile, data)) { error = "Error opening input file"; return false; }
   size_t first = 0;
   uint32_t count = 0;
   if (data.size() >= 4 && std::memcmp(data.data(), "TIS ", 4) == 0) {
@@ -179,13 +316,21 @@ bool encodeMosFile(const Options& options, const std::string& inFile, const std:
   const size_t tableOfs = (size_t)palOfs + (size_t)count * PALETTE_SIZE, dataOfs = tableOfs + (size_t)count * 4;
   if (mos.size() < dataOfs + (size_t)width * height) { error = "Incomplete or corrupted MOS file"; return false; }
 
-  OutputFile out(outFile);
-  if (!out.f) { error = "Error opening output file"; return false; }
   uint8_t header[HEADER_MBC_SIZE];
   std::memcpy(header, "MBC V1.0", 8);
   wr32(header + 8, Options::GetEncodingCode(options.getEncoding(), options.isDeflate()));
   wr32(header + 12, width);
   wr32(header + 16, height);
+  if (slabPipelineApplies(options)) {
+    MosFeed feed(mos, width, height, palOfs);
+    if (!encodeFast(options, feed, outFile, header, sizeof(header), error)) {
+      if (error == "Error while reading tile data") error = "Tile data outside of the MOS file";
+      return false;
+    }
+    return true;
+  }
+  OutputFile out(outFile);
+  if (!out.f) { error = "Error opening output file"; return false; }
   if (std::fwrite(header, 1, sizeof(header), out.f) != sizeof(header)) { error = "Error while writing header"; return false; }
   bool bad = false;
   auto provider = [&](unsigned i) {
