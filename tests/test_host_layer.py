@@ -339,3 +339,89 @@ def test_slab_pipeline_failures_leave_no_output(host, tmp_path):
     open(src, "wb").write(bytes(mos))
     assert host.tcbh_encode_file(src.encode(), dst.encode(), 1, 2, 0, 0, 2) != 0
     assert not os.path.exists(dst)
+
+
+# ---- tileconv -I (N4): container facts printed exactly like TileConv::showInfo ---------------------------------
+INFO_EXPECTED = """Parsing "{d}/h.tis"...
+File type:       TIS
+File subtype:    Paletted
+Number of tiles: 3
+
+Parsing "{d}/n.tis"...
+File type:       TIS (assumed)
+File subtype:    Paletted
+Number of tiles: 3
+
+Parsing "{d}/a.mos"...
+File type:       MOS (compressed)
+File subtype:    Paletted (V1)
+Width:           150
+Height:          70
+Columns:         3
+Rows:            2
+
+Parsing "{d}/c.mos"...
+File type:       MOS (compressed)
+File subtype:    Paletted (V1)
+Width:           150
+Height:          70
+Columns:         3
+Rows:            2
+
+Parsing "{d}/a.tbc"...
+File type:       TBC
+TBC version:     1.0
+Compression:     0x0101 - BC1/DXT1 (uncompressed)
+Number of tiles: 3
+
+Parsing "{d}/a.mbc"...
+File type:       MBC
+MBC version:     1.0
+Compression:     0x0002 - BC2/DXT3 (zlib-compressed)
+Width:           150
+Height:          70
+Number of tiles: 6
+
+Parsing "{d}/a.tiz"...
+File type:       TIZ
+Format version:  0
+Number of tiles: 7
+
+Parsing "{d}/a.moz"...
+File type:       MOZ
+Format version:  0
+Width:           130
+Height:          65
+Number of tiles: 6
+
+Parsing "{d}/x.bin"...
+File type:       Unknown
+
+Parsing "{d}/missing"...
+
+"""
+
+
+def test_info_dump_matches_the_reference(tmp_path):
+    """`-I` needs no GPU.  The expected text was captured from the reference CLI (oracle/_ref/tileconv_ref -I -T ...); where
+    that binary exists the two programs are also compared directly.  (The reference reports every MOS as "compressed":
+    its isMosc flag is never cleared, tileconv.cpp:281-284.)"""
+    d = str(tmp_path)
+    tiles = synth.mixed_tiles(3, 1)
+    write_tis(os.path.join(d, "h.tis"), tiles, header=True)
+    write_tis(os.path.join(d, "n.tis"), tiles, header=False)
+    open(os.path.join(d, "a.mos"), "wb").write(make_mos(150, 70, 5)[0])
+    open(os.path.join(d, "c.mos"), "wb").write(make_mos(150, 70, 5, compressed=True)[0])
+    open(os.path.join(d, "a.tbc"), "wb").write(b"TBC V1.0" + struct.pack("<II", 0x101, 3))
+    open(os.path.join(d, "a.mbc"), "wb").write(b"MBC V1.0" + struct.pack("<III", 2, 150, 70))
+    open(os.path.join(d, "a.tiz"), "wb").write(b"TIZ0" + struct.pack(">H", 7))
+    open(os.path.join(d, "a.moz"), "wb").write(b"MOZ0" + struct.pack(">HH", 130, 65))
+    open(os.path.join(d, "x.bin"), "wb").write(b"hello world")
+    names = ["h.tis", "n.tis", "a.mos", "c.mos", "a.tbc", "a.mbc", "a.tiz", "a.moz", "x.bin", "missing"]
+    cmd = ["-I", "-T"] + [os.path.join(d, n) for n in names]
+    own = subprocess.run([TBC_ENCODE] + cmd, capture_output=True, text=True, timeout=60)
+    assert own.returncode == 0
+    assert own.stdout == INFO_EXPECTED.format(d=d)
+    if os.path.exists(REF_CLI):
+        ref = subprocess.run([REF_CLI] + cmd, capture_output=True, text=True, timeout=60)
+        assert ref.stdout == own.stdout

@@ -1,9 +1,12 @@
 #include "converter_dxt_cuda.h"
 
+#include <atomic>
+#include <cstdio>
 #include <cstring>
 #include <map>
 #include <mutex>
 #include <utility>
+#include <vector>
 
 #include "tcb200.h"
 
@@ -11,25 +14,47 @@ namespace tc {
 
 namespace {
 
-// The reference builds a new converter for every tile (tiledata.cpp:114); creating a CUDA context
-// per tile would dominate, so encoder contexts are cached per calling thread, keyed by
-// (pixel type, encode quality).  Worker threads of the reference's pool each get their own.
-struct ContextCache
+// The reference builds a new converter for every tile (tiledata.cpp:114) and runs convert() on up to 256 pool
+// threads; creating a CUDA context per tile -- or per thread -- would dominate.  Encoder contexts therefore live in one
+// process-wide pool keyed by (pixel type, encode quality): convert() borrows an idle context and returns it, so there
+// are as many contexts as there are tiles in flight at once, and new ones are spread round-robin over the visible
+// devices.  The pool is never torn down (the CUDA runtime may already be gone when static destructors run).
+class ContextPool
 {
-  std::map<std::pair<int, int>, tcb200_ctx*> entries;
-  ~ContextCache() { for (auto& e : entries) tcb200_destroy(e.second); }
-  tcb200_ctx* get(int type, int quality)
+public:
+  tcb200_ctx* acquire(int type, int quality)
   {
-    auto key = std::make_pair(type, quality);
-    auto it = entries.find(key);
-    if (it != entries.end()) return it->second;
-    tcb200_ctx* ctx = tcb200_create(0, type, quality, 16);
-    if (ctx) entries[key] = ctx;
+    {
+      std::lock_guard<std::mutex> lock(m_mutex);
+      std::vector<tcb200_ctx*>& idle = m_idle[std::make_pair(type, quality)];
+      if (!idle.empty()) { tcb200_ctx* ctx = idle.back(); idle.pop_back(); return ctx; }
+    }
+    const int devices = tcb200_device_count();
+    const int device = devices > 0 ? (int)(m_next.fetch_add(1) % (unsigned)devices) : 0;
+    tcb200_ctx* ctx = tcb200_create(device, type, quality, 16);
+    if (ctx == nullptr) {
+      // Converter::convert can only return 0 (converter.h:83); say why once, on stderr
+      std::call_once(m_reported, [] { std::fprintf(stderr, "tileconv_b200: %s\n", tcb200_last_error(nullptr)); });
+    }
     return ctx;
   }
+  void release(int type, int quality, tcb200_ctx* ctx)
+  {
+    std::lock_guard<std::mutex> lock(m_mutex);
+    m_idle[std::make_pair(type, quality)].push_back(ctx);
+  }
+private:
+  std::mutex m_mutex;
+  std::map<std::pair<int, int>, std::vector<tcb200_ctx*>> m_idle;
+  std::atomic<unsigned> m_next{0};
+  std::once_flag m_reported;
 };
 
-thread_local ContextCache t_cache;
+ContextPool& pool()
+{
+  static ContextPool* p = new ContextPool();
+  return *p;
+}
 
 }  // namespace
 
@@ -72,7 +97,8 @@ int ConverterDxtCuda::convert(uint8_t* palette, uint8_t* indexed, uint8_t* encod
   }
   if (width <= 0 || height <= 0 || width > 64 || height > 64 || !isTypeValid()) return 0;
   setWidth(width); setHeight(height);
-  tcb200_ctx* ctx = t_cache.get((int)getType(), getOptions().getEncodingQuality());
+  const int type = (int)getType(), quality = getOptions().getEncodingQuality();
+  tcb200_ctx* ctx = pool().acquire(type, quality);
   if (ctx == nullptr) return 0;
 
   uint8_t record[TCB200_TILE_RECORD];
@@ -80,7 +106,13 @@ int ConverterDxtCuda::convert(uint8_t* palette, uint8_t* indexed, uint8_t* encod
   std::memcpy(record + 1024, indexed, (size_t)width * height);
   const uint16_t wh[2] = { (uint16_t)width, (uint16_t)height };
   uint8_t out[4 + 4096];
-  if (tcb200_encode(ctx, record, wh, 1, out) != TCB200_OK) return 0;
+  const int rc = tcb200_encode(ctx, record, wh, 1, out);
+  if (rc != TCB200_OK) {
+    static std::once_flag reported;
+    std::call_once(reported, [&] { std::fprintf(stderr, "tileconv_b200: GPU encode failed: %s\n", tcb200_last_error(ctx)); });
+  }
+  pool().release(type, quality, ctx);
+  if (rc != TCB200_OK) return 0;
   const int total = getRequiredSpace(width, height) + 4;
   std::memcpy(encoded, out, (size_t)total);
   return total;

@@ -1,10 +1,11 @@
 // tbc_encode -- minimal command line over the host layer: TIS/MOS -> TBC/MBC on the GPU with
 // tileconv's flags for this path (-t 1|2|3, -q <dec><enc> where only the encode digit matters,
-// -u, -T, -j n, -s, -o file).  See tileconv/options.cpp:48,75-219 for the originals.
+// -u, -T, -j n, -s, -o file, -I info only).  See tileconv/options.cpp:48,75-219 for the originals.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "tile_stream.h"
 
@@ -12,7 +13,8 @@ int main(int argc, char** argv)
 {
   tc::Options options;
   std::string input, output;
-  bool silent = false;
+  std::vector<std::string> inputs;
+  bool silent = false, info = false;
   for (int i = 1; i < argc; ++i) {
     const std::string a = argv[i];
     auto next = [&]() -> const char* { return (i + 1 < argc) ? argv[++i] : ""; };
@@ -27,11 +29,17 @@ int main(int argc, char** argv)
     else if (a == "-T") options.setAssumeTis(true);
     else if (a == "-j") options.setThreads(std::atoi(next()));
     else if (a == "-s") silent = true;
+    else if (a == "-I") info = true;
     else if (a == "-o") output = next();
-    else input = a;
+    else { input = a; inputs.push_back(a); }
+  }
+  if (info) {
+    // tileconv.cpp:77-81: with -I every input is described and nothing is converted
+    for (const std::string& file : inputs) { tc::showInfo(file, options.assumeTis()); std::printf("\n"); }
+    return 0;
   }
   if (input.empty()) {
-    std::fprintf(stderr, "usage: tbc_encode [-t 0|1|2|3] [-q -N] [-u] [-T] [-j n] [-s] [-o out] in.tis|in.mos\n");
+    std::fprintf(stderr, "usage: tbc_encode [-t 0|1|2|3] [-q -N] [-u] [-T] [-j n] [-s] [-I] [-o out] in.tis|in.mos\n");
     return 1;
   }
   const tc::InputKind kind = tc::sniffInput(input, options.assumeTis());

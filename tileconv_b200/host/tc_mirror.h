@@ -54,6 +54,22 @@ public:
     }
   }
 
+  static const char* GetEncodingName(int code) noexcept                          // options.cpp:495-522
+  {
+    switch (code) {
+      case ENCODE_RAW: return "Not encoded (zlib-compressed)";
+      case ENCODE_DXT1: return "BC1/DXT1 (zlib-compressed)";
+      case ENCODE_DXT3: return "BC2/DXT3 (zlib-compressed)";
+      case ENCODE_DXT5: return "BC3/DXT5 (zlib-compressed)";
+      case ENCODE_Z: case ENCODE_Z | 256: return "JPEG compressed TIZ/MOZ";
+      case ENCODE_RAW | 256: return "Not encoded (uncompressed)";
+      case ENCODE_DXT1 | 256: return "BC1/DXT1 (uncompressed)";
+      case ENCODE_DXT3 | 256: return "BC2/DXT3 (uncompressed)";
+      case ENCODE_DXT5 | 256: return "BC3/DXT5 (uncompressed)";
+      default: return "Unknown (unknown)";
+    }
+  }
+
   void setEncoding(Encoding type) noexcept { m_encoding = type; }
   Encoding getEncoding() const noexcept { return m_encoding; }
   void setEncodingQuality(int v) noexcept { m_qualityEncoding = v < 0 ? 0 : (v > 9 ? 9 : v); }

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdlib>
+#include <cstdio>
 #include <cstring>
 #include <memory>
 
@@ -78,8 +79,15 @@ TileBatchQueue::~TileBatchQueue() noexcept
 
 void TileBatchQueue::setError(const std::string& msg) noexcept
 {
-  std::lock_guard<std::mutex> lock(m_doneMutex);
-  m_error = msg;
+  bool first;
+  {
+    std::lock_guard<std::mutex> lock(m_doneMutex);
+    first = m_error.empty();
+    m_error = msg;
+  }
+  // The reference's callers only see a size-0 tile and print TileData::getErrorMsg(), which the pool cannot set
+  // for a batch failure (graphics.cpp:127-136): say why on stderr, once per queue, so a CLI user sees the CUDA text.
+  if (first && !msg.empty()) std::fprintf(stderr, "tileconv_b200: GPU encode failed: %s\n", msg.c_str());
 }
 
 std::string TileBatchQueue::lastError() noexcept
@@ -124,7 +132,10 @@ bool TileBatchQueue::ensureContexts(const Options& options) noexcept
       slot.tiles.reserve((size_t)m_slabTiles);
       m_slots.push_back(slot);
     }
-  m_inLimit = (size_t)m_slabTiles * m_slots.size();
+  // Tiles the caller may have queued ahead of the feeder: two slabs, whatever the number of GPUs.  Together with the
+  // slabs in flight that bounds the caller-allocated tiles alive inside the queue to (2 + slots) * slabTiles plus the
+  // finished ones the caller has not drained yet (INTEGRATION.md "Memory").
+  m_inLimit = (size_t)m_slabTiles * 2;
   m_feeder = std::thread(&TileBatchQueue::feederMain, this);
   m_harvester = std::thread(&TileBatchQueue::harvesterMain, this);
   return true;
@@ -252,9 +263,11 @@ void TileBatchQueue::feederMain() noexcept
       std::unique_lock<std::mutex> lock(m_inMutex);
       m_inCv.wait(lock, [this] { return m_stop || m_flush || !m_inQueue.empty(); });
       if (m_stop) return;
-      batch.swap(m_inQueue);
-      flush = m_flush;
-      m_flush = false;
+      // take what fits the slab being filled, not the whole queue: the rest stays under the m_inLimit bound
+      const size_t room = (size_t)m_slabTiles - (acquired ? m_slots[current].tiles.size() : 0);
+      while (!m_inQueue.empty() && batch.size() < room) { batch.push_back(m_inQueue.front()); m_inQueue.pop_front(); }
+      flush = m_flush && m_inQueue.empty();
+      if (flush) m_flush = false;
     }
     m_inSpaceCv.notify_all();
     for (TileDataPtr& tile : batch) {

@@ -211,6 +211,104 @@ InputKind sniffInput(const std::string& path, bool assumeTis) noexcept
   return InputKind::UNKNOWN;
 }
 
+bool showInfo(const std::string& fileName, bool assumeTis) noexcept
+{
+  if (fileName.empty()) return false;
+  std::printf("Parsing \"%s\"...\n", fileName.c_str());
+  std::FILE* f = std::fopen(fileName.c_str(), "rb");
+  if (!f) return false;
+  struct Close { std::FILE* f; ~Close() { std::fclose(f); } } closer{ f };
+  std::fseek(f, 0, SEEK_END);
+  const long fileSize = std::ftell(f);
+  std::fseek(f, 0, SEEK_SET);
+  auto read = [&](void* dst, size_t n) { return std::fread(dst, 1, n, f) == n; };
+  uint8_t sig[4], ver[4], b[16];
+  if (!read(sig, 4)) return false;
+  if (std::memcmp(sig, "TIS ", 4) == 0) {
+    if (!read(ver, 4)) return false;
+    if (std::memcmp(ver, "V1  ", 4) != 0 && std::memcmp(ver, "V2  ", 4) != 0) { std::printf("Invalid TIS version.\n"); return false; }
+    if (!read(b, 8)) return false;
+    const uint32_t tileNum = rd32(b), tileSize = rd32(b + 4);
+    std::printf("File type:       TIS\n");
+    std::printf("File subtype:    %s\n", tileSize == 0x1400 ? "Paletted" : tileSize == 0x000c ? "PVRZ-based" : "Unknown");
+    std::printf("Number of tiles: %d\n", (int)tileNum);
+  } else if (std::memcmp(sig, "MOS ", 4) == 0 || std::memcmp(sig, "MOSC", 4) == 0) {
+    std::vector<uint8_t> mos;
+    if (!read(ver, 4)) return false;
+    if (std::memcmp(sig, "MOSC", 4) == 0) {
+      if (fileSize <= 12) { std::printf("Invalid MOSC size\n"); return false; }
+      if (std::memcmp(ver, "V1  ", 4) != 0) { std::printf("Invalid MOSC version.\n"); return false; }
+      if (!read(b, 4)) return false;
+      const uint32_t mosSize = rd32(b);
+      if (mosSize < 24) { std::printf("MOS size too small.\n"); return false; }
+      std::vector<uint8_t> packed((size_t)fileSize - 12);
+      if (!read(packed.data(), packed.size())) { std::printf("Incomplete or corrupted MOSC file.\n"); return false; }
+      mos.resize(mosSize);
+      uLongf got = mosSize;
+      if (uncompress(mos.data(), &got, packed.data(), (uLong)packed.size()) != Z_OK || got != mosSize) {
+        std::printf("Error while decompressing MOSC input file.\n");
+        return false;
+      }
+    } else {
+      if (fileSize < 24) { std::printf("MOS size too small\n"); return false; }
+      mos.resize(24);
+      std::fseek(f, 0, SEEK_SET);
+      if (!read(mos.data(), 24)) return false;
+    }
+    // the reference never clears its isMosc flag (tileconv.cpp:281,284), so plain MOS files are reported as
+    // "compressed" too; kept, since -I output is compared byte for byte
+    std::printf("File type:       MOS (%s)\n", "compressed");
+    if (std::memcmp(mos.data() + 4, "V1  ", 4) == 0) std::printf("File subtype:    Paletted (V1)\n");
+    else if (std::memcmp(mos.data() + 4, "V2  ", 4) == 0) std::printf("File subtype:    PVRZ-based (V2)\n");
+    else std::printf("File version:    Unknown\n");
+    std::printf("Width:           %d\n", (int)rd16(mos.data() + 8));
+    std::printf("Height:          %d\n", (int)rd16(mos.data() + 10));
+    std::printf("Columns:         %d\n", (int)rd16(mos.data() + 12));
+    std::printf("Rows:            %d\n", (int)rd16(mos.data() + 14));
+  } else if (std::memcmp(sig, "TBC ", 4) == 0) {
+    if (!read(ver, 4)) return false;
+    if (std::memcmp(ver, "V1.0", 4) != 0) { std::printf("Invalid or unsupported TBC version.\n"); return false; }
+    if (!read(b, 8)) return false;
+    const uint32_t compType = rd32(b), tileNum = rd32(b + 4);
+    std::printf("File type:       TBC\n");
+    std::printf("TBC version:     1.0\n");
+    std::printf("Compression:     0x%04x - %s\n", compType, Options::GetEncodingName((int)compType));
+    std::printf("Number of tiles: %d\n", (int)tileNum);
+  } else if (std::memcmp(sig, "MBC ", 4) == 0) {
+    if (!read(ver, 4)) return false;
+    if (std::memcmp(ver, "V1.0", 4) != 0) { std::printf("Invalid or unsupported MBC version.\n"); return false; }
+    if (!read(b, 12)) return false;
+    const uint32_t compType = rd32(b), width = rd32(b + 4), height = rd32(b + 8);
+    std::printf("File type:       MBC\n");
+    std::printf("MBC version:     1.0\n");
+    std::printf("Compression:     0x%04x - %s\n", compType, Options::GetEncodingName((int)compType));
+    std::printf("Width:           %d\n", (int)width);
+    std::printf("Height:          %d\n", (int)height);
+    std::printf("Number of tiles: %d\n", (int)(((width + 63) >> 6) * ((height + 63) >> 6)));
+  } else if (std::memcmp(sig, "TIZ0", 4) == 0) {
+    if (!read(b, 2)) return false;
+    std::printf("File type:       TIZ\n");
+    std::printf("Format version:  0\n");
+    std::printf("Number of tiles: %d\n", (int)((b[0] << 8) | b[1]));           // big endian
+  } else if (std::memcmp(sig, "MOZ0", 4) == 0) {
+    if (!read(b, 4)) return false;
+    const int width = (b[0] << 8) | b[1], height = (b[2] << 8) | b[3];
+    std::printf("File type:       MOZ\n");
+    std::printf("Format version:  0\n");
+    std::printf("Width:           %d\n", width);
+    std::printf("Height:          %d\n", height);
+    std::printf("Number of tiles: %d\n", ((width + 63) >> 6) * ((height + 63) >> 6));
+  } else if (assumeTis && (fileSize % 5120) == 0) {
+    std::printf("File type:       TIS (assumed)\n");
+    std::printf("File subtype:    Paletted\n");
+    std::printf("Number of tiles: %d\n", (int)(fileSize / 5120));
+  } else {
+    std::printf("File type:       Unknown\n");
+    return false;
+  }
+  return true;
+}
+
 bool encodeTisFile(const Options& options, const std::string& inFile, const std::string& outFile, std::string& error) noexcept
 {
   if (inFile.empty() || outFile.empty() || inFile == outFile) { error = "Error opening input file"; return false; }

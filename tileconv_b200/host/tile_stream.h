@@ -19,6 +19,11 @@ InputKind sniffInput(const std::string& path, bool assumeTis) noexcept;
 bool encodeTisFile(const Options& options, const std::string& inFile, const std::string& outFile, std::string& error) noexcept;
 bool encodeMosFile(const Options& options, const std::string& inFile, const std::string& outFile, std::string& error) noexcept;
 
+// tileconv -I: prints the container facts of one file exactly like TileConv::showInfo (tileconv/tileconv.cpp:247-440)
+// -- TIS / MOS / MOSC / TBC / MBC / TIZ / MOZ headers and the headerless-TIS guess under -T.  false where the
+// reference returns false (unreadable, truncated or unknown files).
+bool showInfo(const std::string& fileName, bool assumeTis) noexcept;
+
 }  // namespace tc
 
 #endif
