@@ -140,7 +140,7 @@ encode_tiles_kernel(const uint8_t* __restrict__ tiles, const uint16_t* __restric
             construct_ordering(sc, lane, n, x, y, z, wgt, principle[0], principle[1], principle[2], 0);
             EarlySweep early;
             const uint32_t* cand4 = g_tables.cand + g_tables.off4[n];
-            early.r = run_sweep<4, VARIANT>(sc, lane, n, cand4, g_tables.cnt4[n], vp, nullptr);
+            early.r = run_sweep<4, VARIANT>(sc, lane, n, cand4, g_tables.cnt4[n], vp);
             early.entry = 0u;
             if (early.r.c != kNoCandidate) early.entry = sweep_endpoints<4, VARIANT>(sc, n, cand4, early.r.c, early.win, vp);
             cluster_fit<3, VARIANT>(sc, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, true, nullptr, best, vp);

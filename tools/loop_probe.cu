@@ -32,8 +32,8 @@ __global__ void __launch_bounds__(256) sweep_kernel(const uint32_t* __restrict__
   float acc = 0.f; int accC = 0;
   for (int r = 0; r < reps; ++r) {
     SweepResult s;
-    if (ncol == 4) s = run_sweep<4, false>(sc, lane, n, cand, ncand, vp, nullptr);
-    else { Candidate w; s = run_sweep<3, false>(sc, lane, n, cand, ncand, vp, &w); acc += w.a[0]; }
+    if (ncol == 4) s = run_sweep<4, false>(sc, lane, n, cand, ncand, vp);
+    else s = run_sweep<3, false>(sc, lane, n, cand, ncand, vp);
     acc += s.err; accC += s.c;
   }
   out[blockIdx.x * blockDim.x + threadIdx.x] = acc + (float)accC;
