@@ -134,20 +134,19 @@ encode_tiles_kernel(const uint8_t* __restrict__ tiles, const uint16_t* __restric
         FitResult best;
         best.err = FLT_MAX; best.block = make_uint2(0u, 0u);
         if (TYPE == 1) {
-          if (disabled == 0u) {
-            // Compress3 then Compress4 both start from the principal-axis ordering: build it once and
-            // take the 4-colour sweep of iteration 0 while its prefix table is in place.
-            construct_ordering(sc, lane, n, x, y, z, wgt, principle[0], principle[1], principle[2], 0);
-            EarlySweep early;
+          // Compress3, then Compress4 unless a pixel is transparent.  Both start from the principal-axis ordering: it is
+          // built once and the 4-colour sweep of iteration 0 is taken while its prefix table is in place.
+          const bool opaque = disabled == 0u;
+          construct_ordering(sc, lane, n, x, y, z, wgt, principle[0], principle[1], principle[2], 0);
+          EarlySweep early;
+          if (opaque) {
             const uint32_t* cand4 = g_tables.cand + g_tables.off4[n];
             early.r = run_sweep<4, VARIANT>(sc, lane, n, cand4, g_tables.cnt4[n], vp);
             early.entry = 0u;
             if (early.r.c != kNoCandidate) early.entry = sweep_endpoints<4, VARIANT>(sc, n, cand4, early.r.c, early.win, vp);
-            cluster_fit<3, VARIANT>(sc, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, true, nullptr, best, vp);
-            cluster_fit<4, VARIANT>(sc, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, true, &early, best, vp);
-          } else {
-            cluster_fit<3, VARIANT>(sc, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, false, nullptr, best, vp);
           }
+          cluster_fit<3, VARIANT>(sc, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, true, nullptr, best, vp);
+          if (opaque) cluster_fit<4, VARIANT>(sc, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, true, &early, best, vp);
         } else {
           cluster_fit<4, VARIANT>(sc, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, false, nullptr, best, vp);
         }
