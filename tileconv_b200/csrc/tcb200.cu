@@ -140,15 +140,15 @@ encode_tiles_kernel(const uint8_t* __restrict__ tiles, const uint16_t* __restric
           construct_ordering(sc, lane, n, x, y, z, wgt, principle[0], principle[1], principle[2], 0);
           EarlySweep early;
           if (opaque) {
-            const uint32_t* cand4 = g_tables.cand + g_tables.off4[n];
-            early.r = run_sweep<4, VARIANT>(sc, lane, n, cand4, g_tables.cnt4[n], vp);
-            early.entry = 0u;
+            const uint2* cand4 = g_tables.cand + g_tables.off4[n];
+            early.r = run_sweep<4, VARIANT, true>(sc, lane, n, cand4, g_tables.cnt4[n], vp);
+            early.entry = make_uint2(0u, 0u);
             if (early.r.c != kNoCandidate) early.entry = sweep_endpoints<4, VARIANT>(sc, n, cand4, early.r.c, early.win, vp);
           }
-          cluster_fit<3, VARIANT>(sc, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, true, nullptr, best, vp);
-          if (opaque) cluster_fit<4, VARIANT>(sc, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, true, &early, best, vp);
+          cluster_fit<3, VARIANT, true>(sc, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, true, nullptr, best, vp);
+          if (opaque) cluster_fit<4, VARIANT, true>(sc, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, true, &early, best, vp);
         } else {
-          cluster_fit<4, VARIANT>(sc, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, false, nullptr, best, vp);
+          cluster_fit<4, VARIANT, false>(sc, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, false, nullptr, best, vp);
         }
         if (lane == 0) {
           uint32_t* dstColour = T.out + 1 + kWords * ticket + (TYPE == 1 ? 0 : 2);
@@ -389,7 +389,7 @@ static bool build_tables(DeviceTables& h)
     for (int i = 0; i < n; ++i)
       for (int j = (i == 0 ? 1 : i); j <= n; ++j) {
         if (pos >= capacity) return false;
-        h.cand[pos++] = (uint32_t)(rowoff(0) + i) | ((uint32_t)(rowoff(i) + (j - i)) << 8);
+        h.cand[pos++] = make_candidate(rowoff(0) + i, rowoff(i) + (j - i), 0);
       }
     h.cnt3[n] = pos - h.off3[n];
     h.off4[n] = pos;
@@ -397,8 +397,7 @@ static bool build_tables(DeviceTables& h)
       for (int j = i; j <= n; ++j)
         for (int k = (j == 0 ? 1 : j); k <= n; ++k) {
           if (pos >= capacity) return false;
-          h.cand[pos++] = (uint32_t)(rowoff(0) + i) | ((uint32_t)(rowoff(i) + (j - i)) << 8) |
-                          ((uint32_t)(rowoff(j) + (k - j)) << 16);
+          h.cand[pos++] = make_candidate(rowoff(0) + i, rowoff(i) + (j - i), rowoff(j) + (k - j));
         }
     h.cnt4[n] = pos - h.off4[n];
   }

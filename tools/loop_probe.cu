@@ -10,7 +10,7 @@
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "CUDA %s @%d\n", cudaGetErrorString(e_), __LINE__); exit(1);} } while (0)
 using namespace tcb;
 
-__global__ void __launch_bounds__(256) sweep_kernel(const uint32_t* __restrict__ cand, int ncand, int n, int reps, float* out, int ncol)
+__global__ void __launch_bounds__(256) sweep_kernel(const uint2* __restrict__ cand, int ncand, int n, int reps, float* out, int ncol)
 {
   extern __shared__ __align__(16) uint8_t smem[];
   WarpScratch& sc = reinterpret_cast<WarpScratch*>(smem)[threadIdx.x >> 5];
@@ -32,8 +32,8 @@ __global__ void __launch_bounds__(256) sweep_kernel(const uint32_t* __restrict__
   float acc = 0.f; int accC = 0;
   for (int r = 0; r < reps; ++r) {
     SweepResult s;
-    if (ncol == 4) s = run_sweep<4, false>(sc, lane, n, cand, ncand, vp);
-    else s = run_sweep<3, false>(sc, lane, n, cand, ncand, vp);
+    if (ncol == 4) s = run_sweep<4, false, true>(sc, lane, n, cand, ncand, vp);
+    else s = run_sweep<3, false, true>(sc, lane, n, cand, ncand, vp);
     acc += s.err; accC += s.c;
   }
   out[blockIdx.x * blockDim.x + threadIdx.x] = acc + (float)accC;
@@ -69,7 +69,7 @@ static float time_ms(void (*launch)(void*), void* arg)
   return best;
 }
 
-struct Args { const uint32_t* cand; int ncand, n, reps, grid, ncol; size_t smem; float* out; };
+struct Args { const uint2* cand; int ncand, n, reps, grid, ncol; size_t smem; float* out; };
 static void launch_sweep(void* p) { Args* a = (Args*)p; sweep_kernel<<<a->grid, 256, a->smem>>>(a->cand, a->ncand, a->n, a->reps, a->out, a->ncol); }
 static void launch_calib(void* p) { Args* a = (Args*)p; calib_kernel<<<a->grid, 256>>>(a->reps, a->out, 1.0f); }
 
@@ -80,15 +80,15 @@ int main()
   float* out; CK(cudaMalloc(&out, (size_t)sms * 8 * 256 * sizeof(float)));
   for (int ncol = 4; ncol >= 3; --ncol)
   for (int n : { 16, 12, 8 }) {
-    std::vector<uint32_t> list;
+    std::vector<uint2> list;
     if (ncol == 4) {
       for (int i = 0; i < n; ++i) for (int j = i; j <= n; ++j) for (int k = (j == 0 ? 1 : j); k <= n; ++k)
-        list.push_back((uint32_t)(rowoff(0) + i) | ((uint32_t)(rowoff(i) + (j - i)) << 8) | ((uint32_t)(rowoff(j) + (k - j)) << 16));
+        list.push_back(make_candidate(rowoff(0) + i, rowoff(i) + (j - i), rowoff(j) + (k - j)));
     } else {
       for (int i = 0; i < n; ++i) for (int j = (i == 0 ? 1 : i); j <= n; ++j)
-        list.push_back((uint32_t)(rowoff(0) + i) | ((uint32_t)(rowoff(i) + (j - i)) << 8));
+        list.push_back(make_candidate(rowoff(0) + i, rowoff(i) + (j - i), 0));
     }
-    uint32_t* dCand; CK(cudaMalloc(&dCand, list.size() * 4)); CK(cudaMemcpy(dCand, list.data(), list.size() * 4, cudaMemcpyHostToDevice));
+    uint2* dCand; CK(cudaMalloc(&dCand, list.size() * sizeof(uint2))); CK(cudaMemcpy(dCand, list.data(), list.size() * sizeof(uint2), cudaMemcpyHostToDevice));
     const int rounds = ((int)list.size() + 31) / 32;
     for (int ctas : { 1, 2, 3, 4, 6, 8 }) {          // resident CTAs per SM (8 warps each) = 2*ctas warps per SMSP
       Args a; a.cand = dCand; a.ncand = (int)list.size(); a.n = n; a.ncol = ncol; a.reps = (ncol == 4 ? 4000 : 20000) * 16 / n; a.grid = sms * ctas; a.out = out;
