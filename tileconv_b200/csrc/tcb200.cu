@@ -202,22 +202,66 @@ pal_to_argb_kernel(const uint8_t* __restrict__ tiles, int ntiles, uint32_t* __re
 // 251-430), one thread per 4x4 block, pixels written as B,G,R,A (ColorFormat::ARGB) at row pitch w.
 // refBc3Alpha mimics the reference's BC3 alpha decode, which reads its endpoints and index bits two
 // bytes late (converter_dxt.cpp:351-359); 0 decodes BC3 alpha per the format.
+//
+// The kernel is integer-ALU bound, not store bound (ncu, round 2: ALU pipe 81 % with one select chain per pixel), so
+// the pixels are produced four at a time with byte permutes: the block's palette is kept per CHANNEL (the four
+// entries' bytes in one register), the sixteen 2-bit codes are spread into nibbles once, and one PRMT per channel
+// picks a whole pixel row; eight more PRMTs interleave the channel rows into B,G,R,A pixels.  BC3's 3-bit alpha
+// indices and BC2's 4-bit alphas go through the same row-wise selection.
+__device__ __forceinline__ uint32_t spread_2bit_to_nibbles(uint32_t x)       // 8 codes (16 bits) -> 8 nibbles
+{
+  x &= 0xffffu;
+  x = (x | (x << 8)) & 0x00ff00ffu;
+  x = (x | (x << 4)) & 0x0f0f0f0fu;
+  x = (x | (x << 2)) & 0x33333333u;
+  return x;
+}
+__device__ __forceinline__ uint32_t spread_3bit_to_nibbles(uint32_t x)       // 8 indices (24 bits) -> 8 nibbles
+{
+  x = (x & 0x00000fffu) | ((x & 0x00fff000u) << 4);
+  x = (x & 0x003f003fu) | ((x & 0x0fc00fc0u) << 2);
+  x = (x & 0x07070707u) | ((x & 0x38383838u) << 1);
+  return x;
+}
+__device__ __forceinline__ uint32_t spread_nibbles_to_bytes(uint32_t x)     // 4 nibbles (16 bits) -> 4 bytes
+{
+  x &= 0xffffu;
+  x = (x | (x << 8)) & 0x00ff00ffu;
+  x = (x | (x << 4)) & 0x0f0f0f0fu;
+  return x;
+}
+
 template <int TYPE>
 __global__ void __launch_bounds__(kThreads)
 decode_tiles_kernel(const uint8_t* __restrict__ records, int ntiles, int stride, uint32_t* __restrict__ bgra, int refBc3Alpha)
 {
   constexpr int kWords = BlockWords<TYPE>::value;
+  const int b = threadIdx.x;
+  // The header and this thread's block are requested first thing, both at once (a record always spans the full stride
+  // of 256 blocks, so the block's words need not wait for the header); when a CTA is given more than one tile, the
+  // next tile's loads are issued before the current one is decoded.  Launched with one CTA per tile (decode_grid).
+  uint32_t nextHeader = 0u, nextWords[kWords];
+  if ((int)blockIdx.x < ntiles) {
+    const uint32_t* rec = reinterpret_cast<const uint32_t*>(records + (size_t)blockIdx.x * stride);
+    nextHeader = __ldg(rec);
+#pragma unroll
+    for (int k = 0; k < kWords; ++k) nextWords[k] = __ldg(rec + 1 + kWords * b + k);
+  }
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const uint32_t* rec = reinterpret_cast<const uint32_t*>(records + (size_t)tile * stride);
-    const uint32_t header = __ldg(rec);
+    const uint32_t header = nextHeader;
+    uint32_t words[kWords];
+#pragma unroll
+    for (int k = 0; k < kWords; ++k) words[k] = nextWords[k];
+    if (tile + (int)gridDim.x < ntiles) {
+      const uint32_t* rec = reinterpret_cast<const uint32_t*>(records + (size_t)(tile + gridDim.x) * stride);
+      nextHeader = __ldg(rec);
+#pragma unroll
+      for (int k = 0; k < kWords; ++k) nextWords[k] = __ldg(rec + 1 + kWords * b + k);
+    }
     const int w = (int)(header & 0xffffu), h = (int)(header >> 16);
     if (w <= 0 || h <= 0 || w > 64 || h > 64) continue;
     const int bw = (w + 3) >> 2, bh = (h + 3) >> 2;
-    const int b = threadIdx.x;
     if (b >= bw * bh) continue;
-    uint32_t words[kWords];
-#pragma unroll
-    for (int k = 0; k < kWords; ++k) words[k] = __ldg(rec + 1 + kWords * b + k);
     const uint32_t ends = words[kWords - 2], codes = words[kWords - 1];
     const uint32_t c0 = ends & 0xffffu, c1 = ends >> 16;
     // unpackColors565: 5/6/5 bits replicated into 8
@@ -225,22 +269,28 @@ decode_tiles_kernel(const uint8_t* __restrict__ records, int ntiles, int stride,
     e0[0] = ((c0 << 3) & 0xf8u) | ((c0 >> 2) & 0x07u); e0[1] = ((c0 >> 3) & 0xfcu) | ((c0 >> 9) & 0x03u); e0[2] = ((c0 >> 8) & 0xf8u) | ((c0 >> 13) & 0x07u);
     e1[0] = ((c1 << 3) & 0xf8u) | ((c1 >> 2) & 0x07u); e1[1] = ((c1 >> 3) & 0xfcu) | ((c1 >> 9) & 0x03u); e1[2] = ((c1 >> 8) & 0xf8u) | ((c1 >> 13) & 0x07u);
     const bool four = (TYPE != 1) || c0 > c1;
-    uint32_t pal[4];
-    pal[0] = e0[0] | (e0[1] << 8) | (e0[2] << 16) | 0xff000000u;
-    pal[1] = e1[0] | (e1[1] << 8) | (e1[2] << 16) | 0xff000000u;
-    if (four) {
-      pal[2] = ((2 * e0[0] + e1[0]) / 3) | (((2 * e0[1] + e1[1]) / 3) << 8) | (((2 * e0[2] + e1[2]) / 3) << 16) | 0xff000000u;
-      pal[3] = ((e0[0] + 2 * e1[0]) / 3) | (((e0[1] + 2 * e1[1]) / 3) << 8) | (((e0[2] + 2 * e1[2]) / 3) << 16) | 0xff000000u;
-    } else {
-      pal[2] = ((e0[0] + e1[0]) >> 1) | (((e0[1] + e1[1]) >> 1) << 8) | (((e0[2] + e1[2]) >> 1) << 16) | 0xff000000u;
-      pal[3] = 0u;
-    }
-    // alpha
-    uint32_t alpha[16];
-    if (TYPE == 2) {
+    // per-channel palettes: byte k = value of palette entry k (0: endpoint 0, 1: endpoint 1, 2 and 3: interpolants)
+    uint32_t chan[3];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) { uint32_t a = (words[i >> 3] >> (4 * (i & 7))) & 0xfu; alpha[i] = a | (a << 4); }
-    } else if (TYPE == 3) {
+    for (int c = 0; c < 3; ++c) {
+      const uint32_t p2 = four ? (2 * e0[c] + e1[c]) / 3 : (e0[c] + e1[c]) >> 1;
+      const uint32_t p3 = four ? (e0[c] + 2 * e1[c]) / 3 : 0u;
+      chan[c] = e0[c] | (e1[c] << 8) | (p2 << 16) | (p3 << 24);
+    }
+    // row selectors: nibble k of sel[r] = palette entry of pixel k of row r
+    const uint32_t selLo = spread_2bit_to_nibbles(codes), selHi = spread_2bit_to_nibbles(codes >> 16);
+    const uint32_t sel[4] = { selLo, selLo >> 16, selHi, selHi >> 16 };       // PRMT reads the low 16 bits
+
+    // alpha of each pixel row, one byte per pixel
+    uint32_t arow[4];
+    if (TYPE == 1) {
+      const uint32_t pa = four ? 0xffffffffu : 0x00ffffffu;     // entry 3 of the 3-colour mode is transparent black
+#pragma unroll
+      for (int r = 0; r < 4; ++r) arow[r] = __byte_perm(pa, 0u, sel[r]);
+    } else if (TYPE == 2) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) arow[r] = spread_nibbles_to_bytes(words[r >> 1] >> (16 * (r & 1))) * 17u;   // a | a << 4
+    } else {
       // bytes of the block as one 128-bit little-endian value
       const uint64_t lo = (uint64_t)words[0] | ((uint64_t)words[1] << 32), hi = (uint64_t)words[2] | ((uint64_t)words[3] << 32);
       const uint64_t v = refBc3Alpha ? ((lo >> 16) | (hi << 48)) : lo;       // start two bytes late in the quirk mode
@@ -255,26 +305,27 @@ decode_tiles_kernel(const uint8_t* __restrict__ records, int ntiles, int stride,
         for (int k = 1; k < 5; ++k) table[1 + k] = ((5 - k) * a0 + k * a1) / 5;
         table[6] = 0u; table[7] = 255u;
       }
-      const uint64_t ctrl = v >> 16;
-      // the 8 table bytes live in two registers; PRMT picks byte `idx` of the pair in one instruction
+      // the 8 table bytes live in two registers; PRMT picks, per pixel, byte `index` of the pair
       const uint32_t tabLo = table[0] | (table[1] << 8) | (table[2] << 16) | (table[3] << 24);
       const uint32_t tabHi = table[4] | (table[5] << 8) | (table[6] << 16) | (table[7] << 24);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const uint32_t idx = (uint32_t)(ctrl >> (3 * i)) & 7u;
-        alpha[i] = __byte_perm(tabLo, tabHi, idx) & 0xffu;
-      }
+      const uint64_t ctrl = v >> 16;                             // 16 x 3-bit indices
+      const uint32_t idxLo = spread_3bit_to_nibbles((uint32_t)ctrl & 0x00ffffffu);
+      const uint32_t idxHi = spread_3bit_to_nibbles((uint32_t)(ctrl >> 24) & 0x00ffffffu);
+      arow[0] = __byte_perm(tabLo, tabHi, idxLo); arow[1] = __byte_perm(tabLo, tabHi, idxLo >> 16);
+      arow[2] = __byte_perm(tabLo, tabHi, idxHi); arow[3] = __byte_perm(tabLo, tabHi, idxHi >> 16);
     }
+
     const int bx = b % bw, by = b / bw;
     uint32_t* dst = bgra + (size_t)tile * 4096;
     uint32_t px[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const uint32_t code = (codes >> (2 * i)) & 3u;
-      uint32_t v = pal[0];
-      v = code == 1u ? pal[1] : v; v = code == 2u ? pal[2] : v; v = code == 3u ? pal[3] : v;
-      if (TYPE != 1) v = (v & 0x00ffffffu) | (alpha[i] << 24);
-      px[i] = v;
+    for (int r = 0; r < 4; ++r) {
+      const uint32_t wb = __byte_perm(chan[0], 0u, sel[r]), wg = __byte_perm(chan[1], 0u, sel[r]), wr = __byte_perm(chan[2], 0u, sel[r]);
+      // channel rows (B0 B1 B2 B3), (G..), (R..), (A..) -> pixels (B,G,R,A)
+      const uint32_t bg01 = __byte_perm(wb, wg, 0x5140), bg23 = __byte_perm(wb, wg, 0x7362);
+      const uint32_t ra01 = __byte_perm(wr, arow[r], 0x5140), ra23 = __byte_perm(wr, arow[r], 0x7362);
+      px[4 * r + 0] = __byte_perm(bg01, ra01, 0x5410); px[4 * r + 1] = __byte_perm(bg01, ra01, 0x7632);
+      px[4 * r + 2] = __byte_perm(bg23, ra23, 0x5410); px[4 * r + 3] = __byte_perm(bg23, ra23, 0x7632);
     }
     if ((w & 3) == 0 && 4 * by + 3 < h) {
       // whole block inside the tile and rows 16-byte aligned: one 128-bit store per pixel row; a warp
@@ -517,6 +568,15 @@ bool build_rcpps_table(std::vector<uint32_t>& table, int& bits)
     if (ok) return true;
   }
   return false;
+}
+
+// decode_tiles_kernel: one CTA per tile.  Persistent CTAs striding over the tiles were measured 6-20 % slower at every
+// grid size tried (8 ... 256 per SM): the hardware's CTA scheduler balances the SMs better than a static stride, and
+// the write stream leaves no time to amortise anything per CTA.
+int decode_grid(const tcb200_ctx* ctx, int tiles)
+{
+  (void)ctx;
+  return tiles;
 }
 
 int launch_encode(tcb200_ctx* ctx, const uint8_t* dTiles, const uint16_t* dWh, int n, uint8_t* dOut, cudaStream_t stream)
@@ -922,7 +982,7 @@ int tcb200_decode(tcb200_ctx* ctx, const uint8_t* records, int n, uint8_t* bgra,
     if (e == cudaSuccess) e = cudaMemsetAsync(dPix, 0, (size_t)m * 4096 * 4, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->dOut[0], records + (size_t)first * ctx->stride, (size_t)m * ctx->stride, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) {
-      const int grid = m < ctx->sms * 16 ? m : ctx->sms * 16;      // persistent CTAs: 16 per SM, grid-stride over tiles
+      const int grid = decode_grid(ctx, m);
       if (ctx->type == 1) decode_tiles_kernel<1><<<grid, kThreads, 0, st>>>(ctx->dOut[0], m, ctx->stride, dPix, reference_bc3_alpha);
       else if (ctx->type == 2) decode_tiles_kernel<2><<<grid, kThreads, 0, st>>>(ctx->dOut[0], m, ctx->stride, dPix, reference_bc3_alpha);
       else decode_tiles_kernel<3><<<grid, kThreads, 0, st>>>(ctx->dOut[0], m, ctx->stride, dPix, reference_bc3_alpha);
@@ -946,9 +1006,9 @@ float tcb200_time_decode_ms(tcb200_ctx* ctx, const void* d_records, int n, void*
   for (int r = 0; r < reps; ++r) {
     const uint8_t* rec = (const uint8_t*)d_records;
     uint32_t* pix = (uint32_t*)d_bgra;
-    if (ctx->type == 1) decode_tiles_kernel<1><<<(n < ctx->sms * 16 ? n : ctx->sms * 16), kThreads, 0, st>>>(rec, n, ctx->stride, pix, reference_bc3_alpha);
-    else if (ctx->type == 2) decode_tiles_kernel<2><<<(n < ctx->sms * 16 ? n : ctx->sms * 16), kThreads, 0, st>>>(rec, n, ctx->stride, pix, reference_bc3_alpha);
-    else decode_tiles_kernel<3><<<(n < ctx->sms * 16 ? n : ctx->sms * 16), kThreads, 0, st>>>(rec, n, ctx->stride, pix, reference_bc3_alpha);
+    if (ctx->type == 1) decode_tiles_kernel<1><<<decode_grid(ctx, n), kThreads, 0, st>>>(rec, n, ctx->stride, pix, reference_bc3_alpha);
+    else if (ctx->type == 2) decode_tiles_kernel<2><<<decode_grid(ctx, n), kThreads, 0, st>>>(rec, n, ctx->stride, pix, reference_bc3_alpha);
+    else decode_tiles_kernel<3><<<decode_grid(ctx, n), kThreads, 0, st>>>(rec, n, ctx->stride, pix, reference_bc3_alpha);
     ctx->launches.fetch_add(1);
   }
   if (cudaGetLastError() != cudaSuccess || cudaEventRecord(ctx->t1, st) != cudaSuccess) return (float)TCB200_E_CUDA;
