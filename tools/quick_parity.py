@@ -11,9 +11,13 @@ def main():
             "S-C": synth.corner_case_tiles(n)}
     rag, wh = synth.ragged_tiles(n)
     bad = 0
-    for t in (1, 2, 3):
-        for q in (0, 2, 3, 5, 7, 9):
-            with Encoder(t, q) as enc:
+    variants = {"default": {}, "perceptual+sse": dict(metric=pyoracle.PERCEPTUAL, sse=True)}
+    for vname, kw in variants.items():
+      pyoracle.set_variant(kw.get("metric"), kw.get("sse", False))
+      print("== variant", vname)
+      for t in (1, 2, 3):
+        for q in ((0, 1, 2, 3, 5, 7, 8, 9) if vname == "default" else (2, 4, 9)):
+            with Encoder(t, q, **kw) as enc:
                 for name, tiles in sets.items():
                     t0 = time.time(); got = enc.encode(tiles); dt = time.time() - t0
                     want = pyoracle.encode_tiles(tiles, t, q, threads=16)
@@ -31,6 +35,7 @@ def main():
                     nd += int((got[i, :sz] != want[i, :sz]).any())
                 print(f"type {t} q {q} ragged: tiles differing {nd}/{n}")
                 bad += nd
+    pyoracle.set_variant(None, False)
     print("TOTAL BAD", bad)
     return 1 if bad else 0
 
