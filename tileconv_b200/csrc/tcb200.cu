@@ -38,7 +38,7 @@ encode_tiles_kernel(const uint8_t* __restrict__ tiles, const uint16_t* __restric
                     uint8_t* __restrict__ out, int outStride, const Variant vp, unsigned* __restrict__ badTiles)
 {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  typedef TileShared<TYPE> Tile;
+  typedef TileShared<TYPE, WEIGHT_ALPHA> Tile;
   Tile& T = *reinterpret_cast<Tile*>(smem_raw);
   WarpJobs* allJobs = reinterpret_cast<WarpJobs*>(smem_raw + sizeof(Tile));
   WarpScratch* allScratch = reinterpret_cast<WarpScratch*>(smem_raw + sizeof(Tile) + sizeof(WarpJobs) * kWarps);
@@ -48,6 +48,9 @@ encode_tiles_kernel(const uint8_t* __restrict__ tiles, const uint16_t* __restric
   constexpr int kWords = BlockWords<TYPE>::value;
 
   T.unit[tid] = (float)tid / 255.0f;
+  if (tid < 17) T.sqrtw[tid] = sqrtf((float)tid);
+  if (WEIGHT_ALPHA)
+    for (int i = tid; i < 17 * 17; i += kThreads) T.sqrtwa[i] = sqrtf(((float)((i / 17) << 8) + (float)(i % 17)) * (1.0f / 256.0f));
 
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     // ---- stage the tile record: 320 x 128-bit coalesced loads -----------------------------------
@@ -85,7 +88,7 @@ encode_tiles_kernel(const uint8_t* __restrict__ tiles, const uint16_t* __restric
       if (TYPE == 3) { uint2 a = alpha_dxt5(px); dstBlock[0] = a.x; dstBlock[1] = a.y; }
       uint32_t* dstColour = dstBlock + (TYPE == 1 ? 0 : 2);
 
-      const BlockSet s = build_colour_set<TYPE, WEIGHT_ALPHA>(px, jobs, lane);
+      const BlockSet s = build_colour_set<TYPE, WEIGHT_ALPHA, MODE == kRange>(px, jobs, lane);
       if (s.count == 1) {
         uint2 c = single_colour_block<TYPE>(T, jobs.key[0][lane], s, s.disabled != 0u);
         dstColour[0] = c.x; dstColour[1] = c.y;
@@ -127,7 +130,7 @@ encode_tiles_kernel(const uint8_t* __restrict__ tiles, const uint16_t* __restric
         if (lane < n) {
           const uint32_t k = jb.key[lane][slot];
           x = T.unit[k & 255u]; y = T.unit[(k >> 8) & 255u]; z = T.unit[(k >> 16) & 255u];
-          wgt = point_weight<WEIGHT_ALPHA>(k, mask);
+          wgt = point_weight<WEIGHT_ALPHA>(T, k, mask);
         }
         const float principle[3] = { jb.axis[0][slot], jb.axis[1][slot], jb.axis[2][slot] };
         const uint32_t remapLo = jb.remapLo[slot], remapHi = jb.remapHi[slot], disabled = (TYPE == 1) ? mask : 0u;
@@ -699,7 +702,7 @@ tcb200_ctx* tcb200_create_ex(int device, int type, int quality, int max_batch_ti
     }
   }
 
-  const size_t tileBytes = (type == 1) ? sizeof(TileShared<1>) : sizeof(TileShared<2>);
+  const size_t tileBytes = (type == 1) ? sizeof(TileShared<1, false>) : (ctx->weightAlpha ? sizeof(TileShared<2, true>) : sizeof(TileShared<2, false>));
   ctx->smemBytes = tileBytes + sizeof(WarpJobs) * kWarps + (ctx->mode == kRange ? 0 : sizeof(WarpScratch) * kWarps);
   KernelFn fn = select_kernel(ctx->type, ctx->weightAlpha, ctx->mode, ctx->general);
   if (!fn) { fail(nullptr, TCB200_E_ARG, "this build of libtcb200 does not contain the requested kernel"); tcb200_destroy(ctx); return nullptr; }

@@ -15,10 +15,10 @@ mix = np.zeros((2 * B, 5120), np.uint8); bench.fill_batch(mix, pool, 0)
 sets = {"mix": mix, "S-U": np.concatenate([synth.uniform_tiles(512, 1)] * (B // 512)), "S-G": np.concatenate([synth.smooth_tiles(512, 2)] * (B // 512)),
         "S-K": np.concatenate([synth.keyed_tiles(512, 3)] * (B // 512))}
 out = {}
-for (t, q) in ((1, 9), (3, 9)):
+for (t, q) in ((1, 9), (3, 9), (1, 2)):
     enc = Encoder(t, q)
     for name, tiles in sets.items():
-        if t == 3 and name == "mix": continue
+        if (t == 3 and name == "mix") or (q == 2 and name not in ("mix", "S-K")): continue
         n = len(tiles)
         d_in = torch.from_numpy(tiles.reshape(-1)).cuda(); d_out = torch.zeros(n * enc.stride, dtype=torch.uint8, device="cuda")
         torch.cuda.synchronize()
@@ -26,7 +26,7 @@ for (t, q) in ((1, 9), (3, 9)):
         torch.cuda.synchronize()
         ms = min(enc.time_kernel_ms(d_in.data_ptr(), None, n, d_out.data_ptr(), 3) for _ in range(2))
         h = hashlib.sha1(d_out.cpu().numpy().tobytes()).hexdigest()[:10]
-        out[f"bc{t}_{name}"] = [n / (ms * 1e-3), h]
+        out[f"bc{t}{'q2' if q == 2 else ''}_{name}"] = [n / (ms * 1e-3), h]
         del d_in, d_out
     enc.close()
 print(json.dumps(out))
