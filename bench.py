@@ -536,7 +536,8 @@ def main() -> int:
 
     for name, m in modes.items():
         if "roofline" in m:          # decode kernels: HBM
-            m["roofline"].update({"peak": hbm_peak, "frac": m["roofline"]["achieved"] / hbm_peak, "peak_source": f"MEASURED_PEAKS.json ({hbm_src})"})
+            m["roofline"].update({"peak": hbm_peak, "frac": m["roofline"]["achieved"] / hbm_peak, "peak_source": f"MEASURED_PEAKS.json ({hbm_src})",
+                                  "note": "the peak is a COPY measurement (half reads, half writes); this stream is 89 % writes and may exceed it"})
             continue
         t_, q_ = int(name[2]), int(name[-1])
         st = m.pop("_stride")

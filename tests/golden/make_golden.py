@@ -19,6 +19,8 @@ from oracle import pyoracle  # noqa: E402
 from tileconv_b200 import synth  # noqa: E402
 
 CONFIGS = [(t, q) for t in (1, 2, 3) for q in (0, 2, 3, 4, 5, 6, 7, 9)]
+# the libsquish <= 1.10 default metric (squish_oracle_set_variant): host independent, unlike the SSE reciprocal
+PERCEPTUAL_CONFIGS = [(1, 2), (1, 9), (2, 4), (3, 7)]
 
 
 def main():
@@ -43,6 +45,9 @@ def main():
             r = pyoracle.ref_encode_tile(rag[i, :1024], rag[i, 1024:1024 + w * h], w, h, t, q)
             recs[i, :len(r)] = r
         out[f"ragged_t{t}_q{q}"] = recs
+    with pyoracle.variant(metric=pyoracle.PERCEPTUAL):
+        for t, q in PERCEPTUAL_CONFIGS:
+            out[f"perceptual_t{t}_q{q}"] = pyoracle.ref_encode_tiles(tiles, t, q, threads=4)
     path = os.path.join(ROOT, "tests", "golden", "encode_golden.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")
