@@ -108,14 +108,17 @@ bool TileBatchQueue::ensureContexts(const Options& options) noexcept
   m_type = pixelTypeOf(options);
   m_quality = options.getEncodingQuality();
   m_deflate = options.isDeflate();
-  int devices = tcb200_device_count();
-  if (m_maxGpus > 0) devices = std::min(devices, m_maxGpus);
-  if (devices <= 0 || m_type == 0) {
-    setError(devices <= 0 ? "no CUDA device (there is no CPU fallback)" : "pixel type is not BC1/BC2/BC3");
+  const int visible = tcb200_device_count();
+  // m_maxGpus (TCB200_GPUS) = number of encoder contexts.  Normally <= the visible devices; a larger value puts
+  // several contexts on one device (round-robin), which only adds slabs in flight -- it is how the multi-context
+  // paths of the queue are exercised on a one-GPU box.
+  int devices = m_maxGpus > 0 ? std::min(m_maxGpus, 64) : visible;
+  if (visible <= 0 || m_type == 0) {
+    setError(visible <= 0 ? "no CUDA device (there is no CPU fallback)" : "pixel type is not BC1/BC2/BC3");
     return false;
   }
   for (int d = 0; d < devices; ++d) {
-    tcb200_ctx* ctx = tcb200_create(d, m_type, m_quality, m_slabTiles);
+    tcb200_ctx* ctx = tcb200_create(d % visible, m_type, m_quality, m_slabTiles);
     if (ctx == nullptr) {
       setError(tcb200_last_error(nullptr));
       for (Gpu& g : m_gpus) tcb200_destroy(g.ctx);
