@@ -425,3 +425,48 @@ def test_info_dump_matches_the_reference(tmp_path):
     if os.path.exists(REF_CLI):
         ref = subprocess.run([REF_CLI] + cmd, capture_output=True, text=True, timeout=60)
         assert ref.stdout == own.stdout
+
+
+# ---- container validation and the no-fallback rule need no GPU --------------------------------------------------------
+def test_driver_rejects_malformed_containers_before_touching_the_gpu(host, tmp_path):
+    """Header checks of readTIS / readMOS (tileconv/graphics.cpp:773-973): every malformed input is refused with the
+    reference's message and leaves no output file."""
+    tiles = synth.mixed_tiles(2, 7)
+    body = tiles.tobytes()
+    cases = [
+        (b"TIS V9  " + struct.pack("<IIII", 2, 0x1400, 0x18, 0x40) + body, 0, b"Invalid TIS version"),
+        (b"TIS V1  " + struct.pack("<IIII", 0, 0x1400, 0x18, 0x40) + body, 0, b"No tiles found"),
+        (b"TIS V1  " + struct.pack("<IIII", 2, 0x000c, 0x18, 0x40) + body, 0, b"Invalid tile size"),
+        (b"TIS V1  " + struct.pack("<IIII", 2, 0x1400, 0x10, 0x40) + body, 0, b"Invalid header size"),
+        (b"TIS V1  " + struct.pack("<IIII", 2, 0x1400, 0x18, 0x20) + body, 0, b"Invalid tile dimensions"),
+        (b"TIS V1  " + struct.pack("<IIII", 3, 0x1400, 0x18, 0x40) + body, 0, b"Incomplete TIS file"),
+        (b"TIS V1  " + struct.pack("<II", 2, 0x1400), 0, b"Invalid TIS header"),
+        (body[:-1], 1, b"Unsupported input file"),                   # headerless but not a multiple of 5120 bytes
+        (body, 0, b"Unsupported input file"),                        # headerless without -T
+        (b"MOS V2  " + bytes(40), 0, b"Unsupported MOS version"),
+        (b"MOS V1  " + struct.pack("<HHHHII", 0, 64, 1, 1, 0x40, 24) + bytes(5120), 0, b"Invalid MOS dimensions"),
+        (b"MOS V1  " + struct.pack("<HHHHII", 64, 64, 1, 1, 0x20, 24) + bytes(5120), 0, b"Invalid tile dimensions"),
+        (b"MOS V1  " + struct.pack("<HHHHII", 64, 64, 1, 1, 0x40, 24) + bytes(100), 0, b"Incomplete or corrupted MOS file"),
+        (b"MOSC" + b"V1  " + struct.pack("<I", 5000) + b"not a zlib stream", 0, b"Error while decompressing MOSC input file"),
+    ]
+    for k, (blob, assume, message) in enumerate(cases):
+        src, dst = str(tmp_path / f"bad{k}.bin"), str(tmp_path / f"bad{k}.out")
+        open(src, "wb").write(blob)
+        assert host.tcbh_encode_file(src.encode(), dst.encode(), 1, 2, 0, assume, 2) != 0, k
+        assert message in host.tcbh_last_error(), (k, host.tcbh_last_error())
+        assert not os.path.exists(dst), k
+
+
+def test_driver_has_no_cpu_fallback(host, tmp_path):
+    from tileconv_b200 import capi
+    if capi.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    src, dst = str(tmp_path / "ok.tis"), str(tmp_path / "ok.tbc")
+    write_tis(src, synth.mixed_tiles(3, 8), header=True)
+    for route in ("0", "1"):
+        os.environ["TCB200_TILEDATA_ROUTE"] = route
+        try:
+            assert host.tcbh_encode_file(src.encode(), dst.encode(), 1, 9, 0, 0, 2) != 0
+        finally:
+            del os.environ["TCB200_TILEDATA_ROUTE"]
+        assert not os.path.exists(dst)
