@@ -7,9 +7,16 @@ from oracle import pyoracle
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 16
-    sets = {"S-U": synth.uniform_tiles(n), "S-G": synth.smooth_tiles(n), "S-K": synth.keyed_tiles(n),
-            "S-C": synth.corner_case_tiles(n)}
-    rag, wh = synth.ragged_tiles(n)
+    seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0          # 0 = the generators' default seeds
+    if seed:
+        sets = {"S-U": synth.uniform_tiles(n, seed), "S-G": synth.smooth_tiles(n, seed + 1), "S-K": synth.keyed_tiles(n, seed + 2),
+                "S-C": synth.corner_case_tiles(n, seed + 3)}
+        rag, wh = synth.ragged_tiles(n, seed + 4)
+    else:
+        sets = {"S-U": synth.uniform_tiles(n), "S-G": synth.smooth_tiles(n), "S-K": synth.keyed_tiles(n),
+                "S-C": synth.corner_case_tiles(n)}
+        rag, wh = synth.ragged_tiles(n)
+    print("tiles per class", n, "seed", seed)
     bad = 0
     variants = {"default": {}, "perceptual+sse": dict(metric=pyoracle.PERCEPTUAL, sse=True)}
     for vname, kw in variants.items():
