@@ -115,6 +115,11 @@ encode_tiles_kernel(const uint8_t* __restrict__ tiles, const uint16_t* __restric
       __syncthreads();
       WarpScratch& sc = allScratch[warp];
       constexpr int iterations = (MODE == kIterative) ? kMaxIterations : 1;
+      // The pruned sweep (default arithmetic only) keeps one bound term per prefix-table entry: 160 floats per warp in
+      // the tile's palette + index area, which phase A has finished with (the next tile is staged after the final barrier).
+      constexpr bool kPrune = (TCB_PRUNE != 0) && !VARIANT;
+      float* Q = reinterpret_cast<float*>(T.palette) + warp * 160;
+      static_assert(kWarps * 160 * sizeof(float) <= sizeof(T.palette) + sizeof(T.index) && kPrefixEntries <= 160, "Q tables overlay the staged record");
 #pragma unroll 1
       for (;;) {
         int ticket = 0;
@@ -138,20 +143,18 @@ encode_tiles_kernel(const uint8_t* __restrict__ tiles, const uint16_t* __restric
         best.err = FLT_MAX; best.block = make_uint2(0u, 0u);
         if (TYPE == 1) {
           // Compress3, then Compress4 unless a pixel is transparent.  Both start from the principal-axis ordering: it is
-          // built once and the 4-colour sweep of iteration 0 is taken while its prefix table is in place.
+          // built once and the 4-colour sweep of iteration 0 is taken (by the 3-colour fit, right after its own first
+          // sweep) while its tables are in place.
           const bool opaque = disabled == 0u;
-          construct_ordering(sc, lane, n, x, y, z, wgt, principle[0], principle[1], principle[2], 0);
+          construct_ordering<kPrune>(sc, Q, lane, n, x, y, z, wgt, principle[0], principle[1], principle[2], 0);
           EarlySweep early;
-          if (opaque) {
-            const uint2* cand4 = g_tables.cand + g_tables.off4[n];
-            early.r = run_sweep<4, VARIANT, true>(sc, lane, n, cand4, g_tables.cnt4[n], vp);
-            early.entry = make_uint2(0u, 0u);
-            if (early.r.c != kNoCandidate) early.entry = sweep_endpoints<4, VARIANT>(sc, n, cand4, early.r.c, early.win, vp);
-          }
-          cluster_fit<3, VARIANT, true>(sc, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, true, nullptr, best, vp);
-          if (opaque) cluster_fit<4, VARIANT, true>(sc, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, true, &early, best, vp);
+          cluster_fit<3, VARIANT, true, kPrune>(sc, Q, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, true, nullptr,
+                                                opaque ? &early : nullptr, best, vp);
+          if (opaque) cluster_fit<4, VARIANT, true, kPrune>(sc, Q, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, true, &early,
+                                                            nullptr, best, vp);
         } else {
-          cluster_fit<4, VARIANT, false>(sc, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, false, nullptr, best, vp);
+          cluster_fit<4, VARIANT, false, kPrune>(sc, Q, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, false, nullptr,
+                                                 nullptr, best, vp);
         }
         if (lane == 0) {
           uint32_t* dstColour = T.out + 1 + kWords * ticket + (TYPE == 1 ? 0 : 2);
@@ -443,7 +446,7 @@ static bool build_tables(DeviceTables& h)
     for (int i = 0; i < n; ++i)
       for (int j = (i == 0 ? 1 : i); j <= n; ++j) {
         if (pos >= capacity) return false;
-        h.cand[pos++] = make_candidate(rowoff(0) + i, rowoff(i) + (j - i), 0);
+        h.cand[pos++] = make_candidate(rowoff(0) + i, rowoff(i) + (j - i), rowoff(j) + (n - j), 0);
       }
     h.cnt3[n] = pos - h.off3[n];
     h.off4[n] = pos;
@@ -451,7 +454,7 @@ static bool build_tables(DeviceTables& h)
       for (int j = i; j <= n; ++j)
         for (int k = (j == 0 ? 1 : j); k <= n; ++k) {
           if (pos >= capacity) return false;
-          h.cand[pos++] = make_candidate(rowoff(0) + i, rowoff(i) + (j - i), rowoff(j) + (k - j));
+          h.cand[pos++] = make_candidate(rowoff(0) + i, rowoff(i) + (j - i), rowoff(j) + (k - j), rowoff(k) + (n - k));
         }
     h.cnt4[n] = pos - h.off4[n];
   }
