@@ -141,20 +141,19 @@ encode_tiles_kernel(const uint8_t* __restrict__ tiles, const uint16_t* __restric
         const uint32_t remapLo = jb.remapLo[slot], remapHi = jb.remapHi[slot], disabled = (TYPE == 1) ? mask : 0u;
         FitResult best;
         best.err = FLT_MAX; best.block = make_uint2(0u, 0u);
+        float earlyLocal[12];
+        float* early = TCB_EARLY_SMEM ? sc.early : earlyLocal;
         if (TYPE == 1) {
           // Compress3, then Compress4 unless a pixel is transparent.  Both start from the principal-axis ordering: it is
           // built once and the 4-colour sweep of iteration 0 is taken (by the 3-colour fit, right after its own first
           // sweep) while its tables are in place.
           const bool opaque = disabled == 0u;
-          construct_ordering<kPrune>(sc, Q, lane, n, x, y, z, wgt, principle[0], principle[1], principle[2], 0);
-          EarlySweep early;
-          cluster_fit<3, VARIANT, true, kPrune>(sc, Q, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, true, nullptr,
-                                                opaque ? &early : nullptr, best, vp);
-          if (opaque) cluster_fit<4, VARIANT, true, kPrune>(sc, Q, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, true, &early,
-                                                            nullptr, best, vp);
+          construct_ordering<kPrune>(sc, Q, lane, n, x, y, z, wgt, principle[0], principle[1], principle[2], 0,
+                                     (TCB_PRUNE3 != 0 || opaque) && (TCB_PRUNE_MIN == 0 || g_tables.cnt4[n] >= TCB_PRUNE_MIN));
+          cluster_fit<3, VARIANT, true, kPrune, false, true>(sc, Q, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, true, opaque, early, best, vp);
+          if (opaque) cluster_fit<4, VARIANT, true, kPrune, true, false>(sc, Q, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, true, false, early, best, vp);
         } else {
-          cluster_fit<4, VARIANT, false, kPrune>(sc, Q, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, false, nullptr,
-                                                 nullptr, best, vp);
+          cluster_fit<4, VARIANT, false, kPrune, false, false>(sc, Q, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, false, false, early, best, vp);
         }
         if (lane == 0) {
           uint32_t* dstColour = T.out + 1 + kWords * ticket + (TYPE == 1 ? 0 : 2);
@@ -1084,3 +1083,21 @@ double tcb200_fp32_peak(tcb200_ctx* ctx, int fused)
 }
 
 }  // extern "C"
+
+#if TCB_PRUNE_AUDIT
+// Audit build only (tools/prune_audit.py): counters of the pruned sweeps on the current device, then reset.
+// out[0] tested, out[1] skipped, out[2] wrongly skipped (must be 0), out[3] skipped with error below the raw bound,
+// out[4] worst (raw bound - error) / margin over the skipped candidates (must stay below 1).
+extern "C" int tcb200_prune_audit(double* out)
+{
+  unsigned long long c[4] = { 0, 0, 0, 0 };
+  int worst = 0;
+  if (cudaMemcpyFromSymbol(c, tcb::g_pruneAudit, sizeof(c)) != cudaSuccess) return -1;
+  if (cudaMemcpyFromSymbol(&worst, tcb::g_pruneWorst, sizeof(worst)) != cudaSuccess) return -1;
+  for (int i = 0; i < 4; ++i) out[i] = (double)c[i];
+  float w; std::memcpy(&w, &worst, sizeof(w)); out[4] = (double)w;
+  const unsigned long long zero[4] = { 0, 0, 0, 0 }; const int z = 0;
+  cudaMemcpyToSymbol(tcb::g_pruneAudit, zero, sizeof(zero)); cudaMemcpyToSymbol(tcb::g_pruneWorst, &z, sizeof(z));
+  return 0;
+}
+#endif
