@@ -14,6 +14,7 @@ from tileconv_b200 import synth
 pytestmark = pytest.mark.gpu
 
 HOST_THREADS = os.cpu_count() or 8
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def encoder(type_, quality, **kw):
@@ -407,3 +408,23 @@ def test_encode_multi_rejects_mismatched_contexts():
                 encode_multi(bad, tiles.ctypes.data, None, 4, out.ctypes.data)
         with pytest.raises(TcbError):       # bad sizes are caught by the shard's own validation
             encode_multi([a], tiles.ctypes.data, np.array([[0, 1]] * 4, np.uint16).ctypes.data, 4, out.ctypes.data)
+
+
+def test_pruned_sweeps_never_skip_a_candidate_that_could_win():
+    """bc_device.cuh run_sweep skips candidate partitions whose lower bound proves they cannot beat the incumbent.
+    The audit build of the library (-DTCB_PRUNE_AUDIT=1, made by __graft_entry__.build()) evaluates every skipped
+    candidate as well: none may have an error at or below the incumbent, and the rounding shortfall of the bound must
+    stay far inside the margin.  Runs in its own process (the audit build replaces the library)."""
+    import json, subprocess, sys
+    lib = os.path.join(ROOT, "tileconv_b200", "libtcb200_audit.so")
+    assert os.path.exists(lib), "libtcb200_audit.so is missing: run __graft_entry__.build()"
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "prune_audit.py"), "24", "31"], capture_output=True, text=True, timeout=600)
+    rows = [json.loads(l) for l in res.stdout.splitlines() if l.startswith("{")]
+    assert res.returncode == 0 and rows, res.stderr[-800:]
+    assert rows[-1] == {"wrongly_skipped_total": 0}
+    per_class = [r for r in rows if "class" in r]
+    assert len(per_class) == 36
+    assert all(r["wrongly_skipped"] == 0 for r in per_class)
+    assert max(r["worst_shortfall_over_margin"] for r in per_class) < 0.25
+    # the bound does real work: most 4-colour candidates of ordinary tiles are skipped
+    assert all(r["skipped_frac"] > 0.4 for r in per_class if r["class"] in ("S-U", "S-G", "S-K"))

@@ -457,6 +457,8 @@ static bool build_tables(DeviceTables& h)
         }
     h.cnt4[n] = pos - h.off4[n];
   }
+  // the pruned sweep reads (and ignores) up to 128 entries past the end of a list
+  if (pos + 128 > capacity) return false;
   return true;
 }
 

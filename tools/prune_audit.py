@@ -3,13 +3,12 @@
   * skipped candidates whose error was NOT above the incumbent (must be zero: such a candidate could have won),
   * skipped candidates whose binary32 error lies below the raw bound -(sum Q) -- the rounding the margin exists for --
     and the worst such shortfall as a fraction of the margin (must stay below 1; the smaller, the more headroom).
-Build:  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -fmad=false -std=c++17 -shared -Xcompiler -fPIC -DTCB_PRUNE_AUDIT=1 \
-          -o tools/_bin/variants/lib_audit.so tileconv_b200/csrc/tcb200.cu     (on the CPU box)
+Build:  __graft_entry__.build() makes tileconv_b200/libtcb200_audit.so next to the product library.
 Run:    python tools/prune_audit.py [tiles per class] [seed]         (on the GPU box; JSON lines on stdout)"""
 import ctypes, json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-os.environ["TCB200_LIB"] = os.path.join(ROOT, "tools", "_bin", "variants", "lib_audit.so")
+os.environ["TCB200_LIB"] = os.path.join(ROOT, "tileconv_b200", "libtcb200_audit.so")
 import numpy as np
 from tileconv_b200 import Encoder, capi, synth
 
