@@ -576,7 +576,11 @@ def main() -> int:
     main_roof.update({"traffic": traffic,
                       "traffic_note": "DRAM bytes of one launch from the committed ncu capture (profiles/); algorithmic bytes per launch = " + str(bytes_tile * B),
                       "peak_source": "FFMA loop measured live by tcb200_fp32_peak (an FFMA = 2 flops)",
-                      "note": "bit-exactness forbids mul+add fusion, so the attainable ceiling is peak_unfused (separate FMUL/FADD)",
+                      "note": "bit-exactness forbids mul+add fusion, so the ceiling of EXECUTING the reference's arithmetic is peak_unfused (separate "
+                              "FMUL/FADD).  `achieved` counts the reference algorithm's work (the candidates the oracle evaluated on the same tiles); "
+                              "since round 2 the kernel proves by an exact lower bound that most 4-colour candidates cannot win and skips them "
+                              "(bc_device.cuh run_sweep; skipped fractions and the audit of the bound: profiles/r2_prune_audit.jsonl), so "
+                              "frac_of_unfused can exceed 1",
                       "ncu": ncu_facts,      # from the committed capture of this configuration, not measured in this run
                       "classes": {k: {"tiles_per_s": v["tiles_per_s"], "frac": v["roofline"]["frac"], "frac_of_unfused": v["roofline"]["frac_of_unfused"],
                                       "achieved": v["roofline"]["achieved"]} for k, v in classes.items()},

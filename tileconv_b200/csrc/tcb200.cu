@@ -148,7 +148,7 @@ encode_tiles_kernel(const uint8_t* __restrict__ tiles, const uint16_t* __restric
           // built once and the 4-colour sweep of iteration 0 is taken (by the 3-colour fit, right after its own first
           // sweep) while its tables are in place.
           const bool opaque = disabled == 0u;
-          construct_ordering<kPrune>(sc, Q, lane, n, x, y, z, wgt, principle[0], principle[1], principle[2], 0,
+          construct_ordering<kPrune, true>(sc, Q, lane, n, x, y, z, wgt, principle[0], principle[1], principle[2], 0,
                                      (TCB_PRUNE3 != 0 || opaque) && (TCB_PRUNE_MIN == 0 || g_tables.cnt4[n] >= TCB_PRUNE_MIN));
           cluster_fit<3, VARIANT, true, kPrune, false, true>(sc, Q, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, true, opaque, early, best, vp);
           if (opaque) cluster_fit<4, VARIANT, true, kPrune, true, false>(sc, Q, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, true, false, early, best, vp);

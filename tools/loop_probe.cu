@@ -1,4 +1,4 @@
-// loop_probe: the 4-colour candidate loop of bc_device.cuh (run_sweep<4>) in isolation -- every warp sweeps a private,
+// loop_probe: the EXHAUSTIVE 4-colour candidate loop of bc_device.cuh (run_sweep<4, ..., PRUNE = false>) in isolation -- every warp sweeps a private,
 // pre-built prefix table over and over, no fixed work, no tile staging -- at a chosen number of resident warps per
 // SM sub-partition.  Reports SMSP-cycles per row of 32 candidates next to a calibration loop of 128 independent
 // scalar FMULs per row (= 128 FMA-pipe cycles), so that the figure does not depend on knowing the clock.
@@ -32,8 +32,8 @@ __global__ void __launch_bounds__(256) sweep_kernel(const uint2* __restrict__ ca
   float acc = 0.f; int accC = 0;
   for (int r = 0; r < reps; ++r) {
     SweepResult s;
-    if (ncol == 4) s = run_sweep<4, false, true>(sc, lane, n, cand, ncand, vp);
-    else s = run_sweep<3, false, true>(sc, lane, n, cand, ncand, vp);
+    if (ncol == 4) s = run_sweep<4, false, true, false>(sc, nullptr, lane, n, cand, ncand, FLT_MAX, vp);
+    else s = run_sweep<3, false, true, false>(sc, nullptr, lane, n, cand, ncand, FLT_MAX, vp);
     acc += s.err; accC += s.c;
   }
   out[blockIdx.x * blockDim.x + threadIdx.x] = acc + (float)accC;
@@ -83,10 +83,10 @@ int main()
     std::vector<uint2> list;
     if (ncol == 4) {
       for (int i = 0; i < n; ++i) for (int j = i; j <= n; ++j) for (int k = (j == 0 ? 1 : j); k <= n; ++k)
-        list.push_back(make_candidate(rowoff(0) + i, rowoff(i) + (j - i), rowoff(j) + (k - j)));
+        list.push_back(make_candidate(rowoff(0) + i, rowoff(i) + (j - i), rowoff(j) + (k - j), rowoff(k) + (n - k)));
     } else {
       for (int i = 0; i < n; ++i) for (int j = (i == 0 ? 1 : i); j <= n; ++j)
-        list.push_back(make_candidate(rowoff(0) + i, rowoff(i) + (j - i), 0));
+        list.push_back(make_candidate(rowoff(0) + i, rowoff(i) + (j - i), rowoff(j) + (n - j), 0));
     }
     uint2* dCand; CK(cudaMalloc(&dCand, list.size() * sizeof(uint2))); CK(cudaMemcpy(dCand, list.data(), list.size() * sizeof(uint2), cudaMemcpyHostToDevice));
     const int rounds = ((int)list.size() + 31) / 32;
