@@ -32,8 +32,12 @@ template <int TYPE> struct BlockWords { static constexpr int value = (TYPE == 1)
 // metric / SSE-reciprocal knobs read from vp (tcb200_create_ex).  badTiles counts records whose
 // {w,h} is outside 1..64 (only reachable through tcb200_encode_device; the host entry points validate
 // before upload); such a tile gets a zero header and no blocks.
+// Resident CTAs per SM the register allocation aims at: 4 (64 registers) everywhere except the BC2/BC3 cluster kernels,
+// which are 1-2 % faster with 3 (80 registers; measured, profiles/r2_prune_sweeps.log build c3).
+template <int TYPE, int MODE> struct MinCtas { static constexpr int value = (TYPE != 1 && MODE != 0 && TCB_MIN_CTAS == 4) ? 3 : TCB_MIN_CTAS; };
+
 template <int TYPE, bool WEIGHT_ALPHA, int MODE, bool VARIANT>
-__global__ void __launch_bounds__(kThreads, TCB_MIN_CTAS)
+__global__ void __launch_bounds__(kThreads, MinCtas<TYPE, MODE>::value)
 encode_tiles_kernel(const uint8_t* __restrict__ tiles, const uint16_t* __restrict__ wh, int ntiles,
                     uint8_t* __restrict__ out, int outStride, const Variant vp, unsigned* __restrict__ badTiles)
 {
