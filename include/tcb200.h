@@ -186,6 +186,14 @@ long long tcb200_selftest_reciprocal(tcb200_ctx* ctx);
  * TCB200_RECIP_SSE.  The tests compare the result with the CPU instruction itself. */
 int tcb200_selftest_rcpps(tcb200_ctx* ctx, const float* values, int n, float* estimates);
 
+/* Host-side self-test of the candidate tables of the cluster sweeps (no device needed): every list holds exactly the
+ * partitions libsquish's loops visit, in their order (3-colour: i, then j from max(i,1); 4-colour: i, j from i, k from
+ * max(j,1)); every entry's four 16-bit fields are 4 x a prefix-table index <= 152, so that bits 14-15 of a low field
+ * are zero (the kernels read the high field as word >> 14) and the bound-table offsets stay inside the table; and
+ * every list is followed by at least 128 readable entries (the pruned sweep reads ahead).  Returns 0, or the number
+ * of violations. */
+int tcb200_selftest_tables(void);
+
 /* Kernels launched by this context so far (bench.py's gpu_launches). */
 long long tcb200_launch_count(const tcb200_ctx* ctx);
 

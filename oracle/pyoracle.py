@@ -196,6 +196,23 @@ def ref_encode_tiles(tiles: np.ndarray, type_: int, quality: int, threads: int) 
 PERCEPTUAL = (0.2126, 0.7152, 0.0722)   # libsquish <= 1.10's default metric (kColourMetricPerceptual)
 
 
+def bound_audit(tiles: np.ndarray, type_: int, quality: int, scale: float = 0.0) -> dict:
+    """Encodes `tiles` on the calling thread with the bound audit of squish_oracle.cpp switched on: every 4-colour
+    candidate's error is compared with the lower bound the CUDA path prunes by (restated in binary32).  scale = 0
+    uses the CUDA path's margin scale (2^-17)."""
+    lib = oracle()
+    lib.squish_oracle_bound_audit.argtypes = [ctypes.c_int, ctypes.c_float]
+    lib.squish_oracle_bound_audit(1, scale)
+    try:
+        encode_tiles(tiles, type_, quality, threads=1)
+        out = (ctypes.c_double * 5)()
+        lib.squish_oracle_bound_audit_get(out)
+    finally:
+        lib.squish_oracle_bound_audit(0, 0.0)
+    return {"tested": int(out[0]), "skipped": int(out[1]), "wrongly_skipped": int(out[2]), "below_raw_bound": int(out[3]),
+            "worst_shortfall_over_margin": float(out[4])}
+
+
 def set_variant(metric=None, sse: bool = False) -> None:
     """libsquish-version knobs of the restated squish (squish_oracle.cpp header): the metric used when
     the caller passes none, and the SQUISH_USE_SSE arithmetic.  Applies to libtco.so and, when built,

@@ -57,3 +57,8 @@ def test_product_sources_never_touch_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "pyoracle" not in text and "libtco" not in text and "squish_oracle" not in text, f
+
+
+def test_candidate_tables_hold_libsquish_loop_order_and_the_layout_the_kernels_assume():
+    """tcb200_selftest_tables (host only): list contents = the reference's (i,j[,k]) loops, field encoding, read-ahead room."""
+    assert capi.load_library().tcb200_selftest_tables() == 0

@@ -60,6 +60,7 @@ SYMBOLS = [
     ("tcb200_fp32_peak", ctypes.c_double, [ctypes.c_void_p, ctypes.c_int]),
     ("tcb200_selftest_reciprocal", ctypes.c_longlong, [ctypes.c_void_p]),
     ("tcb200_launch_count", ctypes.c_longlong, [ctypes.c_void_p]),
+    ("tcb200_selftest_tables", ctypes.c_int, []),
 ]
 
 

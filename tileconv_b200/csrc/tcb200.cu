@@ -1044,6 +1044,39 @@ float tcb200_time_kernel_ms(tcb200_ctx* ctx, const void* d_tiles, const void* d_
   return ms / (float)reps;
 }
 
+int tcb200_selftest_tables(void)
+{
+  DeviceTables* h = new (std::nothrow) DeviceTables;
+  if (!h) return -1;
+  int bad = build_tables(*h) ? 0 : 1;
+  const int capacity = (int)(sizeof(h->cand) / sizeof(h->cand[0]));
+  auto field_ok = [](uint32_t f) { return (f & 3u) == 0u && f <= 4u * (uint32_t)(kPrefixEntries - 1); };
+  for (int n = 2; n <= 16 && bad == 0; ++n) {
+    int pos = h->off3[n];
+    for (int i = 0; i < n; ++i)
+      for (int j = (i == 0 ? 1 : i); j <= n; ++j, ++pos) {
+        const uint2 c = h->cand[pos];
+        const uint32_t f0 = c.x & 0xffffu, f1 = c.x >> 16, f2 = c.y & 0xffffu;
+        if (!field_ok(f0) || !field_ok(f1) || !field_ok(f2) || (c.x >> 14) != f1 * 4u) ++bad;
+        if ((int)(f0 / 4u) != rowoff(0) + i || (int)(f1 / 4u) != rowoff(i) + (j - i) || (int)(f2 / 4u) != rowoff(j) + (n - j)) ++bad;
+      }
+    if (pos - h->off3[n] != h->cnt3[n]) ++bad;
+    pos = h->off4[n];
+    for (int i = 0; i < n; ++i)
+      for (int j = i; j <= n; ++j)
+        for (int k = (j == 0 ? 1 : j); k <= n; ++k, ++pos) {
+          const uint2 c = h->cand[pos];
+          const uint32_t f0 = c.x & 0xffffu, f1 = c.x >> 16, f2 = c.y & 0xffffu, f3 = c.y >> 16;
+          if (!field_ok(f0) || !field_ok(f1) || !field_ok(f2) || !field_ok(f3) || (c.x >> 14) != f1 * 4u) ++bad;
+          if ((int)(f0 / 4u) != rowoff(0) + i || (int)(f1 / 4u) != rowoff(i) + (j - i) || (int)(f2 / 4u) != rowoff(j) + (k - j) ||
+              (int)(f3 / 4u) != rowoff(k) + (n - k)) ++bad;
+        }
+    if (pos - h->off4[n] != h->cnt4[n] || pos + 128 > capacity) ++bad;
+  }
+  delete h;
+  return bad;
+}
+
 long long tcb200_selftest_reciprocal(tcb200_ctx* ctx)
 {
   if (!ctx) return (long long)TCB200_E_ARG;
