@@ -145,15 +145,14 @@ encode_tiles_kernel(const uint8_t* __restrict__ tiles, const uint16_t* __restric
         const uint32_t remapLo = jb.remapLo[slot], remapHi = jb.remapHi[slot], disabled = (TYPE == 1) ? mask : 0u;
         FitResult best;
         best.err = FLT_MAX; best.block = make_uint2(0u, 0u);
-        float earlyLocal[12];
-        float* early = TCB_EARLY_SMEM ? sc.early : earlyLocal;
+        float early[12];       // the 4-colour sweep the 3-colour fit takes ahead of time: result, entry, endpoints
         if (TYPE == 1) {
           // Compress3, then Compress4 unless a pixel is transparent.  Both start from the principal-axis ordering: it is
           // built once and the 4-colour sweep of iteration 0 is taken (by the 3-colour fit, right after its own first
           // sweep) while its tables are in place.
           const bool opaque = disabled == 0u;
           construct_ordering<kPrune, true>(sc, Q, lane, n, x, y, z, wgt, principle[0], principle[1], principle[2], 0,
-                                     (TCB_PRUNE3 != 0 || opaque) && (TCB_PRUNE_MIN == 0 || g_tables.cnt4[n] >= TCB_PRUNE_MIN));
+                                     TCB_PRUNE3 != 0 || opaque);
           cluster_fit<3, VARIANT, true, kPrune, false, true>(sc, Q, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, true, opaque, early, best, vp);
           if (opaque) cluster_fit<4, VARIANT, true, kPrune, true, false>(sc, Q, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, true, false, early, best, vp);
         } else {
