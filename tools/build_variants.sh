@@ -1,6 +1,8 @@
 #!/bin/bash
 # Builds alternative libtcb200.so files for tools/variant_sweep.py: tools/build_variants.sh name "-DFLAG=1 ..." [name flags]...
 # (development aid; the variants travel to the GPU box with the snapshot, tools/_bin is git-ignored)
+# Knobs of bc_device.cuh: TCB_PRUNE (0 = exhaustive 4-colour sweeps, the `base` build every sweep is hash-checked against),
+# TCB_PRUNE3, TCB_KSCALE (margin scale), TCB_PRUNE_AUDIT, TCB_NO_F32X2, TCB_PACK_*, TCB_MIN_CTAS.
 set -e
 cd "$(dirname "$0")/.."
 mkdir -p tools/_bin/variants
