@@ -423,7 +423,7 @@ def test_pruned_sweeps_never_skip_a_candidate_that_could_win():
     assert res.returncode == 0 and rows, res.stderr[-800:]
     assert rows[-1] == {"wrongly_skipped_total": 0}
     per_class = [r for r in rows if "class" in r]
-    assert len(per_class) == 36
+    assert len(per_class) == 48 and sum(r["variant"] != "default" for r in per_class) == 12      # default and VARIANT kernels
     assert all(r["wrongly_skipped"] == 0 for r in per_class)
     assert max(r["worst_shortfall_over_margin"] for r in per_class) < 0.25
     # the bound does real work: most 4-colour candidates of ordinary tiles are skipped

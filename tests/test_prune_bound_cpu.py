@@ -36,3 +36,19 @@ def test_bound_needs_its_margin_only_for_rounding():
     tiles = np.concatenate([synth.smooth_tiles(6, 99), synth.keyed_tiles(6, 98)])
     a = pyoracle.bound_audit(tiles, 3, 9)
     assert a["wrongly_skipped"] == 0 and a["worst_shortfall_over_margin"] < 0.02
+
+
+@pytest.mark.parametrize("metric,sse", ((pyoracle.PERCEPTUAL, False), (None, True), (pyoracle.PERCEPTUAL, True), ((3.0, 0.5, 2.0), False)))
+def test_bound_holds_for_the_libsquish_version_knobs(metric, sse):
+    """The VARIANT kernels prune too: per-channel metric weights enter the bound terms and widen the margin; the SSE
+    arithmetic only changes how the endpoints are found, which the bound does not depend on."""
+    tiles = np.concatenate([synth.uniform_tiles(2, 71), synth.smooth_tiles(3, 72), synth.keyed_tiles(3, 73), synth.corner_case_tiles(2, 74)])
+    pyoracle.set_variant(metric, sse)
+    try:
+        for type_, quality in ((1, 9), (3, 9)):
+            a = pyoracle.bound_audit(tiles, type_, quality)
+            assert a["tested"] > 10000 and a["skipped"] > 0.3 * a["tested"]
+            assert a["wrongly_skipped"] == 0
+            assert a["worst_shortfall_over_margin"] < 0.25
+    finally:
+        pyoracle.set_variant(None, False)

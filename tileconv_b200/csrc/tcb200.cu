@@ -119,9 +119,9 @@ encode_tiles_kernel(const uint8_t* __restrict__ tiles, const uint16_t* __restric
       __syncthreads();
       WarpScratch& sc = allScratch[warp];
       constexpr int iterations = (MODE == kIterative) ? kMaxIterations : 1;
-      // The pruned sweep (default arithmetic only) keeps one bound term per prefix-table entry: 160 floats per warp in
+      // The pruned sweep keeps one bound term per prefix-table entry: 160 floats per warp in
       // the tile's palette + index area, which phase A has finished with (the next tile is staged after the final barrier).
-      constexpr bool kPrune = (TCB_PRUNE != 0) && !VARIANT;
+      constexpr bool kPrune = (TCB_PRUNE != 0);
       float* Q = reinterpret_cast<float*>(T.palette) + warp * 160;
       static_assert(kWarps * 160 * sizeof(float) <= sizeof(T.palette) + sizeof(T.index) && kPrefixEntries <= 160, "Q tables overlay the staged record");
 #pragma unroll 1
@@ -151,8 +151,9 @@ encode_tiles_kernel(const uint8_t* __restrict__ tiles, const uint16_t* __restric
           // built once and the 4-colour sweep of iteration 0 is taken (by the 3-colour fit, right after its own first
           // sweep) while its tables are in place.
           const bool opaque = disabled == 0u;
-          construct_ordering<kPrune, true>(sc, Q, lane, n, x, y, z, wgt, principle[0], principle[1], principle[2], 0,
-                                     TCB_PRUNE3 != 0 || opaque);
+          construct_ordering<kPrune && !VARIANT, true>(sc, Q, lane, n, x, y, z, wgt, principle[0], principle[1], principle[2], 0,
+                                                       TCB_PRUNE3 != 0 || opaque);
+          if (VARIANT && kPrune && (TCB_PRUNE3 != 0 || opaque)) build_bound_table_metric(sc, Q, lane, n, vp);
           cluster_fit<3, VARIANT, true, kPrune, false, true>(sc, Q, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, true, opaque, early, best, vp);
           if (opaque) cluster_fit<4, VARIANT, true, kPrune, true, false>(sc, Q, lane, n, x, y, z, wgt, principle, iterations, remapLo, remapHi, disabled, true, false, early, best, vp);
         } else {

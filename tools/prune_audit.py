@@ -20,17 +20,19 @@ sets = {"S-U": synth.uniform_tiles(n, seed), "S-G": synth.smooth_tiles(n, seed +
         "S-C": synth.corner_case_tiles(n, seed + 3)}
 out = (ctypes.c_double * 5)()
 total_bad = 0
-for t in (1, 2, 3):
-    for q in (4, 6, 9):
-        with Encoder(t, q) as enc:
-            for name, tiles in sets.items():
-                lib.tcb200_prune_audit(out)          # reset
-                enc.encode(tiles)
-                lib.tcb200_prune_audit(out)
-                row = {"type": t, "quality": q, "class": name, "tiles": n, "tested": int(out[0]), "skipped": int(out[1]),
-                       "skipped_frac": round(out[1] / max(1.0, out[0]), 4), "wrongly_skipped": int(out[2]),
-                       "below_raw_bound": int(out[3]), "worst_shortfall_over_margin": round(out[4], 5)}
-                total_bad += int(out[2])
-                print(json.dumps(row), flush=True)
+PERCEPTUAL = (0.2126, 0.7152, 0.0722)       # libsquish <= 1.10's default metric
+runs = [("default", {}, t, q) for t in (1, 2, 3) for q in (4, 6, 9)]
+runs += [("perceptual+sse", dict(metric=PERCEPTUAL, sse=True), t, q) for (t, q) in ((1, 9), (3, 4), (3, 9))]   # the VARIANT kernels
+for variant, kw, t, q in runs:
+    with Encoder(t, q, **kw) as enc:
+        for name, tiles in sets.items():
+            lib.tcb200_prune_audit(out)          # reset
+            enc.encode(tiles)
+            lib.tcb200_prune_audit(out)
+            row = {"variant": variant, "type": t, "quality": q, "class": name, "tiles": n, "tested": int(out[0]), "skipped": int(out[1]),
+                   "skipped_frac": round(out[1] / max(1.0, out[0]), 4), "wrongly_skipped": int(out[2]),
+                   "below_raw_bound": int(out[3]), "worst_shortfall_over_margin": round(out[4], 5)}
+            total_bad += int(out[2])
+            print(json.dumps(row), flush=True)
 print(json.dumps({"wrongly_skipped_total": total_bad}))
 sys.exit(1 if total_bad else 0)
