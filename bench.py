@@ -169,6 +169,25 @@ def cpu_reference_rate(pool: np.ndarray, sample: int, type_: int, quality: int, 
     return len(tiles) / best, cores, ("reference" if use_ref else "port"), per_tile
 
 
+def cpu_tuned_port_rate(pool: np.ndarray, sample: int, type_: int, quality: int, repeats: int = 3):
+    """The restated squish + tile loop built with -O3 -mavx2 (oracle/libtco_avx2.so; identical results), all cores, best of
+    `repeats`: what a deployment that tunes its CPU build would get.  None where that build or AVX2 is missing."""
+    from oracle import pyoracle
+    if pyoracle.tuned() is None:
+        return None
+    cores = os.cpu_count() or 1
+    tiles = pool[:sample]
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        pyoracle.tuned_encode_tiles(tiles, type_, quality, cores)
+        dt = time.perf_counter() - t0
+        best = dt if best is None or dt < best else best
+    return {"value": len(tiles) / best, "unit": "tiles/s", "cores": cores, "kind": "port",
+            "flags": "-O3 -mavx2 -ffp-contract=off (the reference's Makefile builds with -O2 -msse -mfpmath=sse)",
+            "note": "same restated squish and tile loop, bit-identical output; shows how much of the GPU/CPU ratio is the reference's build flags"}
+
+
 def as_shipped_cli_rate(pool: np.ndarray, sample: int, type_: int, quality: int):
     """BASELINE.md baseline A: the reference CLI as shipped (its own polling thread pool), wall clock of
     `tileconv -s -T -u -t T -q -Q -j 0` on a headerless TIS of `sample` tiles.  None when the CLI was not
@@ -478,6 +497,7 @@ def main() -> int:
     sample = min(args.cpu_sample, POOL_TILES)
     cpu_rate, cores, kind, per_tile = cpu_reference_rate(pool, sample, args.type, args.quality)
     shipped = as_shipped_cli_rate(pool, min(sample, 1024), args.type, args.quality)
+    tuned_port = cpu_tuned_port_rate(pool, sample, args.type, args.quality)
     seam = pool_seam_rate(tiles[:min(B, 65536)], args.type, args.quality) if world == 1 else None
     # parity of the measured outputs: rank 0's first tiles are pool tiles (copy 0)
     want = pyoracle.encode_tiles(pool[:256], args.type, args.quality, threads=cores)
@@ -605,7 +625,7 @@ def main() -> int:
         "roofline": main_roof,
         "cpu_baseline": {"value": cpu_rate, "unit": "tiles/s", "cores": cores, "kind": kind,
                          "sample": f"{sample} pool tiles, {cores} threads over the reference's TileData::encode (-u), restated squish, best of 3 passes",
-                         "as_shipped_cli": shipped},
+                         "as_shipped_cli": shipped, "tuned_port": tuned_port},
         "e2e_pool_seam": seam,
         "parity_spot_check": parity_ok,
         "link": link,

@@ -14,6 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _TCO: Optional[ctypes.CDLL] = None
 _REF: Optional[ctypes.CDLL] = None
+_TUNED: Optional[ctypes.CDLL] = None
 
 
 class Counters(ctypes.Structure):
@@ -44,6 +45,32 @@ def oracle() -> ctypes.CDLL:
         _TCO.tco_pal_to_argb.restype = ctypes.c_int
         _TCO.tco_squish_flags.restype = ctypes.c_int
     return _TCO
+
+
+def tuned() -> Optional[ctypes.CDLL]:
+    """libtco_avx2.so: the restatement built with -O3 -mavx2 (oracle/Makefile), or None if it was not built or this
+    CPU has no AVX2.  Same results bit for bit; only bench.py's cpu_baseline.tuned_port and its test use it."""
+    global _TUNED
+    if _TUNED is None:
+        path = os.path.join(_HERE, "libtco_avx2.so")
+        try:
+            has_avx2 = " avx2 " in open("/proc/cpuinfo").read().replace("\n", " ")
+        except OSError:
+            has_avx2 = False
+        if not has_avx2 or not os.path.exists(path):
+            return None
+        _TUNED = ctypes.CDLL(path)
+    return _TUNED
+
+
+def tuned_encode_tiles(tiles: np.ndarray, type_: int, quality: int, threads: int = 1) -> Optional[np.ndarray]:
+    lib = tuned()
+    if lib is None:
+        return None
+    tiles = np.ascontiguousarray(tiles, np.uint8).reshape(-1, 5120)
+    out = np.zeros((tiles.shape[0], record_size(type_)), np.uint8)
+    lib.tco_encode_tiles(_p(tiles), tiles.shape[0], type_, quality, _p(out), threads)
+    return out
 
 
 def reference() -> Optional[ctypes.CDLL]:
