@@ -140,11 +140,21 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
-def cpu_reference_rate(pool: np.ndarray, sample: int, type_: int, quality: int, repeats: int = 3):
+def cpu_reference_rate(pool: np.ndarray, sample: int, type_: int, quality: int, repeats: int = 3, simd: bool = False):
     """Times the reference's CPU path on all host cores over `sample` tiles, best of `repeats` passes (the first
     one warms the caches and the thread pool up).  Returns (tiles_per_s, cores, kind,
-    counters_per_tile)."""
+    counters_per_tile).  simd = False is the configuration the parity definition names (libsquish's scalar simd_float.h
+    path, SQUISH_USE_SSE = 0, the default of its Makefile build); simd = True evaluates the cluster solve on 4-wide SSE2
+    vectors the way a SQUISH_USE_SSE build lays out its Vec4 (same results here, ~2.3x faster): reported beside it."""
     from oracle import pyoracle
+    pyoracle.set_simd(simd)
+    try:
+        return _cpu_reference_rate(pyoracle, pool, sample, type_, quality, repeats)
+    finally:
+        pyoracle.set_simd(False)
+
+
+def _cpu_reference_rate(pyoracle, pool: np.ndarray, sample: int, type_: int, quality: int, repeats: int):
     cores = os.cpu_count() or 1
     tiles = pool[:sample]
     best = None
@@ -178,14 +188,18 @@ def cpu_tuned_port_rate(pool: np.ndarray, sample: int, type_: int, quality: int,
     cores = os.cpu_count() or 1
     tiles = pool[:sample]
     best = None
-    for _ in range(repeats):
-        t0 = time.perf_counter()
-        pyoracle.tuned_encode_tiles(tiles, type_, quality, cores)
-        dt = time.perf_counter() - t0
-        best = dt if best is None or dt < best else best
+    pyoracle.set_simd(True)
+    try:
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            pyoracle.tuned_encode_tiles(tiles, type_, quality, cores)
+            dt = time.perf_counter() - t0
+            best = dt if best is None or dt < best else best
+    finally:
+        pyoracle.set_simd(False)
     return {"value": len(tiles) / best, "unit": "tiles/s", "cores": cores, "kind": "port",
-            "flags": "-O3 -mavx2 -ffp-contract=off (the reference's Makefile builds with -O2 -msse -mfpmath=sse)",
-            "note": "same restated squish and tile loop, bit-identical output; shows how much of the GPU/CPU ratio is the reference's build flags"}
+            "flags": "-O3 -mavx2 -ffp-contract=off (the reference's Makefile builds with -O2 -msse -mfpmath=sse), SSE2-vector cluster solve",
+            "note": "same restated squish and tile loop, bit-identical output: the fastest CPU build of this algorithm made here"}
 
 
 def as_shipped_cli_rate(pool: np.ndarray, sample: int, type_: int, quality: int):
@@ -270,7 +284,7 @@ def run_reference(args, rank: int, world: int) -> int:
         "cpu_baseline": {"value": value, "unit": "tiles/s", "cores": cores, "kind": kind,
                          "sample": f"{sample} tiles (first of the {POOL_TILES}-tile pool), {cores} std::threads, static partition, "
                                    "each looping the reference's TileData::encode with -u semantics (BASELINE.md baseline B); "
-                                   "squish = restated oracle (libsquish is not vendored by the reference)"},
+                                   "squish = restated oracle (libsquish is not vendored by the reference), scalar simd_float path = the parity definition"},
         "e2e": {"value": value, "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -498,6 +512,7 @@ def main() -> int:
     cpu_rate, cores, kind, per_tile = cpu_reference_rate(pool, sample, args.type, args.quality)
     shipped = as_shipped_cli_rate(pool, min(sample, 1024), args.type, args.quality)
     tuned_port = cpu_tuned_port_rate(pool, sample, args.type, args.quality)
+    simd_rate = cpu_reference_rate(pool, sample, args.type, args.quality, repeats=2, simd=True)[0]
     seam = pool_seam_rate(tiles[:min(B, 65536)], args.type, args.quality) if world == 1 else None
     # parity of the measured outputs: rank 0's first tiles are pool tiles (copy 0)
     want = pyoracle.encode_tiles(pool[:256], args.type, args.quality, threads=cores)
@@ -624,7 +639,11 @@ def main() -> int:
         "clocks": clocks,
         "roofline": main_roof,
         "cpu_baseline": {"value": cpu_rate, "unit": "tiles/s", "cores": cores, "kind": kind,
-                         "sample": f"{sample} pool tiles, {cores} threads over the reference's TileData::encode (-u), restated squish, best of 3 passes",
+                         "sample": f"{sample} pool tiles, {cores} threads over the reference's TileData::encode (-u), restated squish (scalar simd_float path = the "
+                                   "parity definition), best of 3 passes",
+                         "simd_squish": {"value": simd_rate, "unit": "tiles/s",
+                                         "note": "the same run with the cluster solve on 4-wide SSE2 vectors (identical records): the speed of a libsquish "
+                                                 "built with SQUISH_USE_SSE, whose own arithmetic (rcpps) is the `sse` knob of tcb200_create_ex"},
                          "as_shipped_cli": shipped, "tuned_port": tuned_port},
         "e2e_pool_seam": seam,
         "parity_spot_check": parity_ok,

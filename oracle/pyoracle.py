@@ -240,6 +240,15 @@ def bound_audit(tiles: np.ndarray, type_: int, quality: int, scale: float = 0.0)
             "worst_shortfall_over_margin": float(out[4])}
 
 
+def set_simd(on: bool) -> None:
+    """Cluster solve on 4-wide SSE2 vectors (identical results, ~2.3x faster): what a libsquish built with SQUISH_USE_SSE
+    does with its Vec4.  Off by default (the scalar code is the definition); bench.py's CPU arms switch it on.  Applies
+    to libtco.so, libtco_avx2.so and the copy linked into oracle/_ref."""
+    for lib in (oracle(), tuned(), reference()):
+        if lib is not None:
+            lib.squish_oracle_set_simd(1 if on else 0)
+
+
 def set_variant(metric=None, sse: bool = False) -> None:
     """libsquish-version knobs of the restated squish (squish_oracle.cpp header): the metric used when
     the caller passes none, and the SQUISH_USE_SSE arithmetic.  Applies to libtco.so and, when built,
