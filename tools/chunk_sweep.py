@@ -1,3 +1,5 @@
+"""Host-to-host rate of tcb200_encode() against the chunk size (max_batch_tiles) for BC1/BC3 -q 2 and BC1 -q 9: how the
+H2D / kernel / D2H pipeline of one context overlaps.  Development aid (GPU).  usage: python tools/chunk_sweep.py"""
 import sys, os, time
 sys.path.insert(0, os.getcwd())
 import numpy as np, torch

@@ -1,4 +1,9 @@
-import csv, subprocess, sys, collections, io
+"""Instruction and stall-sample share per code REGION of bc_device.cuh (phase A helpers, candidate arithmetic, ordering,
+bound table, bound test, batch evaluation, ...) from the source page of an .ncu-rep captured with --import-source on.
+The regions are found by marker comments in the current source, so run it on a capture of the current build.
+usage: python tools/ncu_regions.py report.ncu-rep"""
+import csv, subprocess, sys, collections, io, os
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep=sys.argv[1]
 txt=subprocess.run(["ncu","-i",rep,"--page","source","--csv","--print-source","cuda,sass"],capture_output=True,text=True).stdout
 rows=list(csv.reader(io.StringIO(txt)))
@@ -17,8 +22,7 @@ for r in rows:
         per[line]+=int(r[ie])
         if r[sm].isdigit(): samp[line]+=int(r[sm])
 # regions from source file line ranges
-import re
-src=open('/root/repo/tileconv_b200/csrc/bc_device.cuh').read().splitlines()
+src=open(os.path.join(ROOT, 'tileconv_b200', 'csrc', 'bc_device.cuh')).read().splitlines()
 def find(pat,start=0):
     for i in range(start,len(src)):
         if pat in src[i]: return i+1
