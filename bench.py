@@ -249,6 +249,27 @@ def pool_seam_rate(tiles: np.ndarray, type_: int, quality: int):
             "note": "bounded by the single-threaded reference caller loop (per-tile heap buffers + ordered drain), not by the GPU"}
 
 
+def pruning_facts(type_: int, quality: int):
+    """Fraction of the 4-colour candidates the kernels skipped by their exact lower bound, per tile class, from the committed
+    audit run (profiles/r2_prune_audit.jsonl: tools/prune_audit.py on the audit build) -- not measured in this run."""
+    if quality <= 2:
+        return None                                                # RangeFit levels: no cluster sweeps
+    group = 9 if quality >= 7 else (6 if quality >= 5 else 4)      # the audit runs one level per quality class
+    out = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_prune_audit.jsonl")) as f:
+            for line in f:
+                r = json.loads(line)
+                if r.get("variant", "default") == "default" and r.get("type") == type_ and r.get("quality") == group and r.get("class") in ("S-U", "S-G", "S-K"):
+                    out[r["class"]] = {"skipped_frac": r["skipped_frac"], "wrongly_skipped": r["wrongly_skipped"]}
+    except Exception:
+        return None
+    if not out:
+        return None
+    out["source"] = "profiles/r2_prune_audit.jsonl (committed audit run, 256 tiles per class)"
+    return out
+
+
 def flops_per_tile(per_tile: dict) -> float:
     """W = C3*138 + C4*160 + F_fixed, F_fixed(n) ~ 30 n + 8*27 per cluster block."""
     return (per_tile["cand3"] * F3_OPS + per_tile["cand4"] * F4_OPS
@@ -617,6 +638,7 @@ def main() -> int:
                               "(bc_device.cuh run_sweep; skipped fractions and the audit of the bound: profiles/r2_prune_audit.jsonl), so "
                               "frac_of_unfused can exceed 1",
                       "ncu": ncu_facts,      # from the committed capture of this configuration, not measured in this run
+                      "pruning": pruning_facts(args.type, args.quality),
                       "classes": {k: {"tiles_per_s": v["tiles_per_s"], "frac": v["roofline"]["frac"], "frac_of_unfused": v["roofline"]["frac_of_unfused"],
                                       "achieved": v["roofline"]["achieved"]} for k, v in classes.items()},
                       "hbm": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,

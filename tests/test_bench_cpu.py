@@ -47,3 +47,11 @@ def test_flop_model_matches_survey_8d():
     import bench
     per_tile = {"cand3": 10.0, "cand4": 100.0, "points": 16.0, "cluster_blocks": 1.0}
     assert bench.flops_per_tile(per_tile) == 10 * 138 + 100 * 160 + 30 * 16 + 216
+
+
+def test_pruning_facts_come_from_the_committed_audit():
+    import bench
+    f = bench.pruning_facts(1, 9)
+    assert f is not None and set(f) >= {"S-U", "S-G", "S-K", "source"}
+    assert all(f[c]["wrongly_skipped"] == 0 and 0.3 < f[c]["skipped_frac"] < 1.0 for c in ("S-U", "S-G", "S-K"))
+    assert bench.pruning_facts(1, 2) is None          # RangeFit levels have no cluster sweeps
